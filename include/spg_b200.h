@@ -1,0 +1,217 @@
+/*
+ * spg_b200.h — C-ABI of libspg_b200.so, the sm_100a implementation of the
+ * superpoint-graph learning hot path of loicland/superpoint_graph.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers, sizes and the
+ * CUDA stream to enqueue on (a `cudaStream_t` passed as `void*`), never
+ * synchronises the host and never throws.  Return value: 0 on success,
+ * a negative SPG_E_* code for an argument the kernels cannot serve, or a
+ * positive `cudaError_t` if the launch failed (see spg_error_string()).
+ *
+ * All matrices are row-major and contiguous unless a leading dimension is
+ * given.  `dtype`: 0 = float32, 1 = float64 (float64 is served by the generic
+ * kernels only; it exists for gradcheck-style tests, reference
+ * learning/ecc/test_GraphConvModule.py:25).
+ *
+ * Each function names the reference code it replaces as
+ * `ref: <file>:<lines>` relative to the reference repository root.
+ */
+#ifndef SPG_B200_H_
+#define SPG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spg_stream_t; /* cudaStream_t */
+
+#define SPG_OK 0
+#define SPG_E_BADARG (-1)      /* null pointer / negative size / bad flag */
+#define SPG_E_UNSUPPORTED (-2) /* shape or dtype not served by any kernel */
+#define SPG_E_ALIGN (-3)       /* pointer or leading dimension misaligned */
+
+#define SPG_F32 0
+#define SPG_F64 1
+
+/* ---------------------------------------------------------------- runtime */
+int spg_version(void);
+const char* spg_error_string(int code);
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream. */
+int spg_zero(void* ptr, int64_t bytes, spg_stream_t stream);
+
+/* Per-kernel launch accounting.  Counting is always on; timing (a pair of CUDA
+ * events recorded around every launch on the launching stream) only while
+ * enabled.  spg_prof_collect() synchronises the recorded events and folds them
+ * into per-kernel totals.                                                    */
+int spg_prof_enable(int on);
+int spg_prof_reset(void);
+int spg_prof_collect(void);
+int spg_prof_num_kernels(void);
+const char* spg_prof_kernel_name(int kernel_id);
+int spg_prof_kernel_stats(int kernel_id, int64_t* launches, double* total_ms);
+int64_t spg_prof_total_launches(void);
+
+/* ------------------------------------------------- edge-conditioned conv  */
+/* Graph structure arrays (all int32, device):
+ *   tgt_rowptr[n_out+1]  exclusive scan of the in-degrees `degs`
+ *                        (ref: learning/ecc/GraphConvInfo.py:56, cuda_kernels.py:123)
+ *   idxn[n_edges]        source node of every edge, edges sorted by target
+ *                        (ref: GraphConvInfo.py:50-52)
+ *   idxe[n_edges]|NULL   row of `w` used by every edge (edge-feature compaction,
+ *                        ref: GraphConvInfo.py:59-62); NULL = identity
+ *   edge_tgt[n_edges]    target node of every edge
+ *   src_rowptr[n_in+1], src_perm[n_edges]
+ *                        CSR over SOURCE nodes: src_perm lists edge ids grouped by
+ *                        source (stable), used for the atomic-free grad_input.   */
+
+/* out[i,:] = (1/deg_i) * sum_{e in in(i)} op(x[idxn_e,:], w[e]) ; 0 if deg_i==0.
+ * w_is_matrix=0: w [n_w_rows,c_in], op = elementwise product (needs c_in==c_out)
+ * w_is_matrix=1: w [n_w_rows,c_in,c_out], op = vector-matrix product.
+ * ref: learning/ecc/GraphConvModule.py:43-94 (GraphConvFunction.forward),
+ *      learning/ecc/cuda_kernels.py:55-86,117-127 (conv_aggregate_fw).        */
+int spg_ecc_fwd(const void* x, const void* w, const int32_t* tgt_rowptr, const int32_t* idxn,
+                const int32_t* idxe, void* out, int64_t n_out, int64_t n_edges, int c_in,
+                int c_out, int w_is_matrix, int dtype, spg_stream_t stream);
+
+/* grad_w[e] (+)= sum_{r<n_iter} op'(x_r[idxn_e,:], g_r[tgt_e,:]/deg_tgt)
+ * with x_r = xs + r*x_iter_stride elements, g_r = gs + r*g_iter_stride elements;
+ * op' = elementwise product (vector filters) or outer product (matrix filters).
+ * n_iter>1 folds the recurrent reuse of one filter bank (ref:
+ * learning/modules.py:160,171-176) into one pass.  With idxe the rows are
+ * accumulated atomically into grad_w, which the caller must have zeroed.
+ * ref: GraphConvModule.py:108-133, cuda_kernels.py:88-114,129-139.             */
+int spg_ecc_bwd_w(const void* xs, const void* gs, int64_t x_iter_stride, int64_t g_iter_stride,
+                  int n_iter, const int32_t* tgt_rowptr, const int32_t* idxn,
+                  const int32_t* idxe, const int32_t* edge_tgt, void* grad_w, int64_t n_out,
+                  int64_t n_edges, int c_in, int c_out, int w_is_matrix, int accumulate,
+                  int dtype, spg_stream_t stream);
+
+/* grad_x[j,:] = add0[j,:] + add1[j,:] + sum_{e: idxn_e=j} op''(w[e], g[tgt_e,:]/deg_tgt)
+ * (add0/add1 may be NULL).  ref: GraphConvModule.py:135-146.                    */
+int spg_ecc_bwd_x(const void* w, const void* g, const int32_t* tgt_rowptr,
+                  const int32_t* src_rowptr, const int32_t* src_perm, const int32_t* edge_tgt,
+                  const int32_t* idxe, const void* add0, const void* add1, void* grad_x,
+                  int64_t n_in, int64_t n_edges, int c_in, int c_out, int w_is_matrix,
+                  int dtype, spg_stream_t stream);
+
+/* ----------------------------------------------------------- GRUCellEx    */
+#define SPG_GRU_LAYERNORM 1
+#define SPG_GRU_INGATE 2
+#define SPG_GRU_BIAS 4
+/* hy = GRUCellEx(x, h).  input_size == hidden_size == H (as built by
+ * learning/graphnet.py:74).  weight_ih/weight_hh [3H,H], bias_* [3H],
+ * ig_weight [H,H], ig_bias [H].  ref: learning/modules.py:205-251.             */
+int spg_gru_fwd(const float* x, const float* h, const float* weight_ih, const float* weight_hh,
+                const float* bias_ih, const float* bias_hh, const float* ig_weight,
+                const float* ig_bias, float* hy, int64_t n_rows, int hidden, int flags,
+                spg_stream_t stream);
+/* Backward of the cell for one step.  Row-local gradients d_x, d_h are final; the
+ * parameter gradients are left as per-row factors for one batched reduction over
+ * all recurrent steps: d_gi, d_gh [n,3H] (grads of the pre-norm gate inputs),
+ * d_q [n,H] (grad of the input-gate pre-activation), xprime [n,H] (gated input),
+ * dpre [n,4H] = [d_pr,d_pz,d_pn,d_pn*r] (bias gradients' summands).             */
+int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const float* weight_ih,
+                const float* weight_hh, const float* bias_ih, const float* bias_hh,
+                const float* ig_weight, const float* ig_bias, float* d_x, float* d_h,
+                float* d_gi, float* d_gh, float* d_q, float* xprime, float* dpre,
+                int64_t n_rows, int hidden, int flags, spg_stream_t stream);
+
+/* ------------------------------------------------------------- dense      */
+/* C[M,N] = opA(A) * opB(B) (+ bias[N]), fp32, FMA accumulation.
+ *   a_kmajor=1: A is [M,K] (ld = lda, K contiguous); 0: A is [K,M] (M contiguous)
+ *   b_kmajor=1: B is [N,K] (ld = ldb, K contiguous); 0: B is [K,N] (N contiguous)
+ * Optional fused prologue (the "BN apply + ReLU of the producing layer"):
+ *   a_scale/a_shift [K] (needs a_kmajor=1): A'[m,k] = f(A[m,k]*a_scale[k]+a_shift[k])
+ *   b_scale/b_shift [N] (needs b_kmajor=0): B'[k,n] = f(B[k,n]*b_scale[n]+b_shift[n])
+ *   f = ReLU if the matching *_relu flag is set (scale may be NULL = 1, shift NULL = 0).
+ * split_k>1 reduces K in `split_k` slices through `workspace`
+ * (>= split_k*M*N floats) and a deterministic second pass.
+ * ref: the nn.Conv1d(k=1)/nn.Linear calls of learning/pointnet.py:29,41,51,85,100
+ *      and learning/graphnet.py:27,32, and their autograd backward.            */
+int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
+             const float* bias, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+             const float* a_scale, const float* a_shift, int a_relu, const float* b_scale,
+             const float* b_shift, int b_relu, int split_k, float* workspace,
+             spg_stream_t stream);
+
+/* Per-column batch statistics of Y[M,C] (ld = ldy): mean[C], biased var[C];
+ * workspace >= 3*C*spg_colstats_chunks(M) floats.  ref: nn.BatchNorm1d in training
+ * mode (learning/pointnet.py:31,43,87,103; learning/graphnet.py:29).            */
+int64_t spg_colstats_chunks(int64_t M);
+int spg_colstats(const float* Y, int64_t ldy, int64_t M, int C, float* mean, float* var,
+                 float* workspace, spg_stream_t stream);
+/* scale = gamma/sqrt(var+eps), shift = beta-mean*scale; if running_* non-NULL:
+ * running = (1-momentum)*running + momentum*{mean, var*M/(M-1)}; if num_batches_tracked
+ * (int64 scalar, device) is non-NULL it is incremented by one.                    */
+int spg_bn_fold(const float* mean, const float* var, const float* gamma, const float* beta,
+                float eps, float* scale, float* shift, float* running_mean, float* running_var,
+                int64_t* num_batches_tracked, float momentum, int64_t M, int C,
+                spg_stream_t stream);
+/* out[m,c] = f(Y[m,c]*scale[c]+shift[c]); scale/shift may be NULL.               */
+int spg_affine_act(const float* Y, int64_t ldy, const float* scale, const float* shift, int relu,
+                   float* out, int64_t ldo, int64_t M, int C, spg_stream_t stream);
+/* Column sums: out[c] = sum_m X[m,c]; workspace >= C*spg_colstats_chunks(M).      */
+int spg_colsum(const float* X, int64_t ldx, int64_t M, int C, float* out, float* workspace,
+               spg_stream_t stream);
+/* Backward of a = relu?(bn?(y)):
+ *   pass 1 (spg_act_bwd_reduce, BN layers only):
+ *       s1[c] = sum_m G*mask, s2[c] = sum_m G*mask*xhat       (= d_beta, d_gamma)
+ *   pass 2 (spg_act_bwd_apply): dY = scale*(G*mask - s1/M - xhat*s2/M)   (BN)
+ *                               dY = G*mask                             (no BN)
+ *   mask = (y*scale+shift > 0) if relu else 1; xhat = (y-mean)*rstd; in-place OK. */
+int spg_act_bwd_reduce(const float* G, int64_t ldg, const float* Y, int64_t ldy,
+                       const float* scale, const float* shift, const float* mean,
+                       const float* var, float eps, int relu, float* s1, float* s2,
+                       float* workspace, int64_t M, int C, spg_stream_t stream);
+int spg_act_bwd_apply(const float* G, int64_t ldg, const float* Y, int64_t ldy,
+                      const float* scale, const float* shift, const float* mean,
+                      const float* var, float eps, int relu, int has_bn, const float* s1,
+                      const float* s2, float* dY, int64_t lddy, int64_t M, int C,
+                      spg_stream_t stream);
+
+/* ------------------------------------------------------------ PointNet    */
+/* clouds [B,F,L] (the reference's NCL layout, learning/spg.py:162) -> rows [B*L, ld]
+ * (point-major, channel contiguous, zero padded to ld).  If T [B,2,2] is given the
+ * first two channels are replaced by (xy^T * T')^T with T' = T (+ I if add_eye: the STN's
+ * "+ identity", ref: learning/pointnet.py:61,121-124).                                   */
+int spg_cloud_rows(const float* clouds, const float* T, int add_eye, float* rows, int64_t ld,
+                   int64_t B, int F, int L, spg_stream_t stream);
+/* pooled[b,c] = max_l f(Y[b*L+l,c]*scale[c]+shift[c]); argmax[b,c] = first maximiser.
+ * Writes into pooled with leading dimension ldp (so that the "global" features can sit
+ * in the same row, ref: learning/pointnet.py:126-132).                              */
+int spg_segmax_fwd(const float* Y, int64_t ldy, const float* scale, const float* shift, int relu,
+                   float* pooled, int64_t ldp, int32_t* argmax, int64_t B, int L, int C,
+                   spg_stream_t stream);
+/* G[b*L+l,c] = (l==argmax[b,c]) ? g_pooled[b,c] : 0 (G fully written).              */
+int spg_segmax_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax, float* G,
+                   int64_t ldG, int64_t B, int L, int C, spg_stream_t stream);
+/* dT[b,i,j] = sum_l xy[b,i,l] * dXrows[b*L+l, j], i,j in {0,1}; clouds is the raw
+ * [B,F,L] input, dXrows has leading dimension ld.                                    */
+int spg_stn_apply_bwd(const float* clouds, const float* dXrows, int64_t ld, float* dT, int64_t B,
+                      int F, int L, spg_stream_t stream);
+/* Row gather / scatter between the [Nv,C] PointNet output and the zero-filled [N,C]
+ * descriptors (ref: learning/pointnet.py:156-157): dst[idx[i],:] = src[i,:] and back. */
+int spg_rows_scatter(const float* src, const int64_t* idx, float* dst, int64_t n_src, int C,
+                     spg_stream_t stream);
+int spg_rows_gather(const float* src, const int64_t* idx, float* dst, int64_t n_dst, int C,
+                    spg_stream_t stream);
+
+/* ---------------------------------------------------------------- step    */
+/* Weighted cross entropy with ignore_index (mean reduction = sum w_y*nll / sum w_y),
+ * ref: learning/main.py:205.  loss_out[0] = loss, d_logits [n,C] = dloss/dlogits.
+ * class_weight may be NULL.  workspace: 16 bytes, 8-byte aligned (zeroed by the call).  */
+int spg_ce_loss(const float* logits, const int64_t* target, const float* class_weight,
+                int64_t ignore_index, float* loss_out, float* d_logits, float* workspace,
+                int64_t n_rows, int C, spg_stream_t stream);
+/* One fused pass over the flat parameter/gradient buffers (ref: learning/main.py:210-213):
+ *   g = clamp(g*grad_scale, -clip, clip) (clip<=0: no clamp); g += wd*p; Adam(m,v,step).  */
+int spg_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_clip, float grad_scale, int64_t step, spg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPG_B200_H_ */

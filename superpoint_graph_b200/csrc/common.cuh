@@ -1,0 +1,80 @@
+// Shared helpers for libspg_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spg_b200.h"
+
+namespace spg {
+
+// Kernel ids for launch accounting (order must match kKernelNames in runtime.cu).
+enum KernelId {
+    K_ECC_VV_FWD = 0,
+    K_ECC_MAT_FWD,
+    K_ECC_GEN_FWD,
+    K_ECC_VV_BWD_W,
+    K_ECC_MAT_BWD_W,
+    K_ECC_GEN_BWD_W,
+    K_ECC_VV_BWD_X,
+    K_ECC_MAT_BWD_X,
+    K_ECC_GEN_BWD_X,
+    K_GRU_FWD,
+    K_GRU_BWD,
+    K_GEMM,
+    K_GEMM_SPLITK_REDUCE,
+    K_COLSTATS_PARTIAL,
+    K_COLSTATS_FINAL,
+    K_BN_FOLD,
+    K_AFFINE_ACT,
+    K_COLSUM_PARTIAL,
+    K_COLSUM_FINAL,
+    K_ACT_BWD_REDUCE,
+    K_ACT_BWD_REDUCE_FINAL,
+    K_ACT_BWD_APPLY,
+    K_CLOUD_ROWS,
+    K_SEGMAX_FWD,
+    K_SEGMAX_BWD,
+    K_STN_APPLY_BWD,
+    K_ROWS_SCATTER,
+    K_ROWS_GATHER,
+    K_CE_LOSS,
+    K_CE_LOSS_FINAL,
+    K_CLAMP_ADAM,
+    K_TC_GEMM,
+    K_COUNT
+};
+
+// Brackets one launch with CUDA events when profiling is enabled; always counts it.
+struct LaunchScope {
+    int kid;
+    cudaStream_t stream;
+    int slot;
+    LaunchScope(int kernel_id, cudaStream_t s);
+    ~LaunchScope();
+};
+
+// cudaGetLastError() -> return code of the C-ABI call.
+inline int launch_status() { return (int)cudaGetLastError(); }
+
+constexpr int kNumSMs = 148;
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) { __stcs(p, v); }
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+}  // namespace spg
+
+#define SPG_LAUNCH(kid, stream_, kernel, grid, block, smem, ...)            \
+    do {                                                                     \
+        ::spg::LaunchScope _scope((kid), (stream_));                         \
+        kernel<<<(grid), (block), (smem), (stream_)>>>(__VA_ARGS__);         \
+    } while (0)

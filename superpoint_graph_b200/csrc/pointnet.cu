@@ -1,0 +1,245 @@
+// PointNet-specific data movement: NCL clouds -> point-major rows (with the spatial
+// transformer applied), segmented max-pool over the points of a superpoint with its
+// argmax, the matching backward scatters, and the descriptor row scatter/gather of
+// CloudEmbedder.
+//
+// Reference semantics: learning/pointnet.py:120-133 (transform + max_pool1d + cat),
+// :147-158 (index_copy_ into zero descriptors).  Segment boundaries are implicit
+// (constant L per superpoint, as the reference's loader guarantees: spg.py:209-214).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace spg {
+
+constexpr int kPtChunk = 128;
+
+// grid (B, ceil(L/128)); block 128.  smem tile [F][129].
+__global__ void __launch_bounds__(kPtChunk)
+cloud_rows_kernel(const float* __restrict__ clouds, const float* __restrict__ T, int add_eye,
+                  float* __restrict__ rows, int64_t ld, int F, int L) {
+    extern __shared__ float tile[];
+    const int64_t b = blockIdx.x;
+    const int l0 = blockIdx.y * kPtChunk;
+    const int nl = min(kPtChunk, L - l0);
+    const float* src = clouds + b * (int64_t)F * L;
+    for (int f = 0; f < F; ++f)
+        for (int l = threadIdx.x; l < nl; l += kPtChunk)
+            tile[f * (kPtChunk + 1) + l] = src[(int64_t)f * L + l0 + l];
+    __syncthreads();
+    if (T && F >= 2) {
+        const float eye = add_eye ? 1.f : 0.f;
+        const float t00 = T[b * 4 + 0] + eye, t01 = T[b * 4 + 1], t10 = T[b * 4 + 2],
+                    t11 = T[b * 4 + 3] + eye;
+        for (int l = threadIdx.x; l < nl; l += kPtChunk) {
+            const float x0 = tile[l], x1 = tile[(kPtChunk + 1) + l];
+            // xy' = xy^T * T  (row vector times T), ref: learning/pointnet.py:123
+            tile[l] = fmaf(x0, t00, x1 * t10);
+            tile[(kPtChunk + 1) + l] = fmaf(x0, t01, x1 * t11);
+        }
+        __syncthreads();
+    }
+    float* dst = rows + (b * L + l0) * ld;
+    const int64_t total = (int64_t)nl * ld;
+    for (int64_t i = threadIdx.x; i < total; i += kPtChunk) {
+        const int l = (int)(i / ld), f = (int)(i % ld);
+        dst[i] = f < F ? tile[f * (kPtChunk + 1) + l] : 0.f;
+    }
+}
+
+// grid (ceil(C/32), B); block (32 x 8).
+__global__ void __launch_bounds__(256)
+segmax_fwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
+                  const float* __restrict__ shift, int relu, float* __restrict__ pooled,
+                  int64_t ldp, int* __restrict__ argmax, int L, int C) {
+    __shared__ float s_v[8][32];
+    __shared__ int s_i[8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
+    const int64_t b = blockIdx.y;
+    float best = -FLT_MAX;
+    int bi = 0;
+    if (c < C) {
+        const float sc = scale ? scale[c] : 1.f, sh = shift ? shift[c] : 0.f;
+        const float* src = Y + b * L * ldy + c;
+        for (int l = y; l < L; l += 8) {
+            float v = fmaf(__ldg(src + (int64_t)l * ldy), sc, sh);
+            if (relu) v = fmaxf(v, 0.f);
+            if (v > best || l == y) {  // first element initialises; strict > keeps first max
+                best = v;
+                bi = l;
+            }
+        }
+    }
+    s_v[y][x] = best;
+    s_i[y][x] = (y < L) ? bi : -1;
+    __syncthreads();
+    if (y == 0 && c < C) {
+        float bv = s_v[0][x];
+        int bidx = s_i[0][x];
+        for (int j = 1; j < 8; ++j) {
+            const float v = s_v[j][x];
+            const int i = s_i[j][x];
+            if (i >= 0 && (v > bv || (v == bv && i < bidx))) {
+                bv = v;
+                bidx = i;
+            }
+        }
+        pooled[b * ldp + c] = bv;
+        argmax[b * C + c] = bidx;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+segmax_bwd_kernel(const float* __restrict__ gp, int64_t ldg, const int* __restrict__ argmax,
+                  float* __restrict__ G, int64_t ldG, int64_t rows, int L, int C) {
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
+    if (c >= C) return;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + y; r < rows; r += (int64_t)gridDim.y * 8) {
+        const int64_t b = r / L;
+        const int l = (int)(r % L);
+        G[r * ldG + c] = (argmax[b * C + c] == l) ? gp[b * ldg + c] : 0.f;
+    }
+}
+
+// grid B; block 128.
+__global__ void __launch_bounds__(128)
+stn_apply_bwd_kernel(const float* __restrict__ clouds, const float* __restrict__ dX, int64_t ld,
+                     float* __restrict__ dT, int F, int L) {
+    __shared__ float red[4][4];
+    const int64_t b = blockIdx.x;
+    const float* xy = clouds + b * (int64_t)F * L;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    for (int l = threadIdx.x; l < L; l += 128) {
+        const float x0 = xy[l], x1 = xy[L + l];
+        const float d0 = dX[(b * L + l) * ld], d1 = dX[(b * L + l) * ld + 1];
+        a00 = fmaf(x0, d0, a00);
+        a01 = fmaf(x0, d1, a01);
+        a10 = fmaf(x1, d0, a10);
+        a11 = fmaf(x1, d1, a11);
+    }
+    a00 = warp_sum(a00);
+    a01 = warp_sum(a01);
+    a10 = warp_sum(a10);
+    a11 = warp_sum(a11);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red[w][0] = a00;
+        red[w][1] = a01;
+        red[w][2] = a10;
+        red[w][3] = a11;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4)
+        dT[b * 4 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] +
+                                  red[3][threadIdx.x];
+}
+
+__global__ void rows_scatter_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                    float* __restrict__ dst, int64_t n, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const int64_t r = i / C;
+    dst[idx[r] * C + (i % C)] = src[i];
+}
+
+__global__ void rows_gather_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                   float* __restrict__ dst, int64_t n, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const int64_t r = i / C;
+    dst[i] = src[idx[r] * C + (i % C)];
+}
+
+}  // namespace spg
+
+using namespace spg;
+
+extern "C" {
+
+int spg_cloud_rows(const float* clouds, const float* T, int add_eye, float* rows, int64_t ld,
+                   int64_t B, int F, int L, spg_stream_t stream) {
+    if (B < 0 || F <= 0 || L <= 0 || ld < F) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!clouds || !rows) return SPG_E_BADARG;
+    if (F > 256 || B > 2147483647ll) return SPG_E_UNSUPPORTED;
+    const size_t smem = sizeof(float) * (size_t)F * (kPtChunk + 1);
+    if (smem > 200 * 1024) return SPG_E_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cloud_rows_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((unsigned)B, (unsigned)ceil_div64(L, kPtChunk));
+    SPG_LAUNCH(K_CLOUD_ROWS, (cudaStream_t)stream, cloud_rows_kernel, grid, kPtChunk, smem, clouds,
+               T, add_eye, rows, ld, F, L);
+    return launch_status();
+}
+
+int spg_segmax_fwd(const float* Y, int64_t ldy, const float* scale, const float* shift, int relu,
+                   float* pooled, int64_t ldp, int32_t* argmax, int64_t B, int L, int C,
+                   spg_stream_t stream) {
+    if (B < 0 || L <= 0 || C <= 0 || ldy < C || ldp < C) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!Y || !pooled || !argmax) return SPG_E_BADARG;
+    if (B > 65535ll * 32768) return SPG_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t max_by = 65535;
+    for (int64_t b0 = 0; b0 < B; b0 += max_by) {
+        const int64_t nb = min(max_by, B - b0);
+        dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)nb);
+        SPG_LAUNCH(K_SEGMAX_FWD, s, segmax_fwd_kernel, grid, 256, 0, Y + b0 * L * ldy, ldy, scale,
+                   shift, relu, pooled + b0 * ldp, ldp, argmax + b0 * C, L, C);
+        int rc = launch_status();
+        if (rc) return rc;
+    }
+    return SPG_OK;
+}
+
+int spg_segmax_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax, float* G,
+                   int64_t ldG, int64_t B, int L, int C, spg_stream_t stream) {
+    if (B < 0 || L <= 0 || C <= 0 || ldg < C || ldG < C) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!g_pooled || !argmax || !G) return SPG_E_BADARG;
+    const int64_t rows = B * L;
+    int64_t gy = ceil_div64(rows, 64);
+    if (gy > 8 * kNumSMs) gy = 8 * kNumSMs;
+    dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)gy);
+    SPG_LAUNCH(K_SEGMAX_BWD, (cudaStream_t)stream, segmax_bwd_kernel, grid, 256, 0, g_pooled, ldg,
+               argmax, G, ldG, rows, L, C);
+    return launch_status();
+}
+
+int spg_stn_apply_bwd(const float* clouds, const float* dXrows, int64_t ld, float* dT, int64_t B,
+                      int F, int L, spg_stream_t stream) {
+    if (B < 0 || F < 2 || L <= 0 || ld < 2) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!clouds || !dXrows || !dT) return SPG_E_BADARG;
+    if (B > 2147483647ll) return SPG_E_UNSUPPORTED;
+    SPG_LAUNCH(K_STN_APPLY_BWD, (cudaStream_t)stream, stn_apply_bwd_kernel, (unsigned)B, 128, 0,
+               clouds, dXrows, ld, dT, F, L);
+    return launch_status();
+}
+
+int spg_rows_scatter(const float* src, const int64_t* idx, float* dst, int64_t n_src, int C,
+                     spg_stream_t stream) {
+    if (n_src < 0 || C <= 0) return SPG_E_BADARG;
+    if (n_src == 0) return SPG_OK;
+    if (!src || !idx || !dst) return SPG_E_BADARG;
+    SPG_LAUNCH(K_ROWS_SCATTER, (cudaStream_t)stream, rows_scatter_kernel,
+               (unsigned)ceil_div64(n_src * C, 256), 256, 0, src, idx, dst, n_src, C);
+    return launch_status();
+}
+
+int spg_rows_gather(const float* src, const int64_t* idx, float* dst, int64_t n_dst, int C,
+                    spg_stream_t stream) {
+    if (n_dst < 0 || C <= 0) return SPG_E_BADARG;
+    if (n_dst == 0) return SPG_OK;
+    if (!src || !idx || !dst) return SPG_E_BADARG;
+    SPG_LAUNCH(K_ROWS_GATHER, (cudaStream_t)stream, rows_gather_kernel,
+               (unsigned)ceil_div64(n_dst * C, 256), 256, 0, src, idx, dst, n_dst, C);
+    return launch_status();
+}
+
+}  // extern "C"

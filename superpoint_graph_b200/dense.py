@@ -1,0 +1,209 @@
+"""Chains of (Linear | Conv1d k=1) [+ BatchNorm1d] [+ ReLU] layers with hand-written forward AND
+backward over the C-ABI kernels.
+
+Only the raw (pre-norm) output of each layer is stored; "BatchNorm apply + ReLU" of a layer is
+deferred and fused into whatever consumes it (the next layer's GEMM operand load, the
+segmented max-pool, or an explicit materialisation at the end of a chain).
+
+Reference semantics: the nn.Sequential stacks built by learning/pointnet.py:27-53,83-118 and
+learning/graphnet.py:17-34 (`create_fnet`), in training mode (batch statistics, running-stat
+update with momentum, biased variance for normalisation / unbiased for the running estimate) and
+in eval mode (running statistics).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class LayerSpec(object):
+    """One parametric layer: names index into the flat parameter list given to the chain."""
+
+    __slots__ = ("w", "b", "gamma", "beta", "bn", "relu", "cin", "cout")
+
+    def __init__(self, w, b, gamma, beta, bn, relu, cin, cout):
+        self.w, self.b, self.gamma, self.beta = w, b, gamma, beta
+        self.bn, self.relu, self.cin, self.cout = bn, relu, cin, cout
+
+
+def parse_sequential(seq, training):
+    """nn.Sequential -> ([LayerSpec], [parameter tensors]).  LayerSpec.w/b/gamma/beta are
+    positions in the returned parameter list; LayerSpec.bn is the BatchNorm module (buffers)."""
+    specs, params = [], []
+    mods = list(seq.children()) if isinstance(seq, nn.Sequential) else list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Conv1d):
+            if m.kernel_size != (1,) or m.stride != (1,) or m.padding != (0,) or m.groups != 1:
+                raise NotImplementedError("only 1x1 Conv1d layers are on the SPG path")
+            cout, cin = m.weight.shape[0], m.weight.shape[1]
+        elif isinstance(m, nn.Linear):
+            cout, cin = m.weight.shape
+        elif isinstance(m, nn.Dropout):
+            if training and m.p > 0:
+                raise NotImplementedError(
+                    "dropout with p>0 in training mode is not implemented by the fused path "
+                    "(the reference's documented configs use ptn_prelast_do=0)")
+            i += 1
+            continue
+        else:
+            raise NotImplementedError("unsupported module in fused chain: %r" % (m,))
+        w = len(params)
+        params.append(m.weight)
+        b = None
+        if m.bias is not None:
+            b = len(params)
+            params.append(m.bias)
+        i += 1
+        bn, gamma, beta, relu = None, None, None, False
+        if i < len(mods) and isinstance(mods[i], nn.BatchNorm1d):
+            bn = mods[i]
+            if bn.affine:
+                gamma = len(params)
+                params.append(bn.weight)
+                beta = len(params)
+                params.append(bn.bias)
+            i += 1
+        elif i < len(mods) and isinstance(mods[i], nn.GroupNorm):
+            raise NotImplementedError("norm='layer'/'group' PointNets are not on the fused path")
+        if i < len(mods) and isinstance(mods[i], nn.ReLU):
+            relu = True
+            i += 1
+        specs.append(LayerSpec(w, b, gamma, beta, bn, relu, cin, cout))
+    return specs, params
+
+
+class Deferred(object):
+    """A raw activation [M, C] (leading dimension ld) plus the affine+ReLU still to be applied."""
+
+    __slots__ = ("raw", "ld", "C", "scale", "shift", "relu")
+
+    def __init__(self, raw, ld, C, scale=None, shift=None, relu=False):
+        self.raw, self.ld, self.C = raw, ld, C
+        self.scale, self.shift, self.relu = scale, shift, relu
+
+    @property
+    def pending(self):
+        return self.scale is not None or self.shift is not None or self.relu
+
+    def aff(self):
+        return (self.scale, self.shift, self.relu) if self.pending else None
+
+    def materialise(self, M):
+        if not self.pending and self.ld == self.C:
+            return self.raw
+        return ops.affine_act(self.raw, self.ld, M, self.C, self.scale, self.shift, self.relu)
+
+
+def _w2d(w):
+    return w.view(w.shape[0], w.shape[1]) if w.dim() == 3 else w
+
+
+def chain_forward(inp, M, specs, params, training, saved=None):
+    """inp: Deferred input.  Returns the Deferred output of the last layer.  If `saved` is a list,
+    per-layer records for chain_backward are appended to it."""
+    cur = inp
+    for sp in specs:
+        W = _w2d(params[sp.w])
+        bias = params[sp.b] if sp.b is not None else None
+        y = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
+                     a_aff=cur.aff())
+        mean = var = scale = shift = None
+        if sp.bn is not None:
+            bn = sp.bn
+            gamma = params[sp.gamma] if sp.gamma is not None else None
+            beta = params[sp.beta] if sp.beta is not None else None
+            if training or not bn.track_running_stats:
+                mean, var = ops.colstats(y, sp.cout, M, sp.cout)
+                rm = rv = nbt = None
+                mom = 0.0
+                if training and bn.track_running_stats:
+                    rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+                    if bn.momentum is None:
+                        raise NotImplementedError("BatchNorm momentum=None (cumulative average)")
+                    mom = bn.momentum
+                scale, shift = ops.bn_fold(mean, var, gamma, beta, bn.eps, rm, rv, mom, M, nbt)
+            else:
+                mean, var = bn.running_mean, bn.running_var
+                scale, shift = ops.bn_fold(mean, var, gamma, beta, bn.eps)
+        nxt = Deferred(y, sp.cout, sp.cout, scale, shift, sp.relu)
+        if saved is not None:
+            saved.append((cur, nxt, mean, var))
+        cur = nxt
+    return cur
+
+
+def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_g=False):
+    """G: gradient w.r.t. the chain's final *activated* output [M, C_last].
+    `grads` (list aligned with params) is filled in place.  Returns the gradient w.r.t. the
+    chain input's activated value [M, cin_0] (or None)."""
+    for li in range(len(specs) - 1, -1, -1):
+        sp = specs[li]
+        cur, nxt, mean, var = saved[li]
+        C = sp.cout
+        if sp.bn is not None:
+            eps = sp.bn.eps
+            s1, s2 = ops.act_bwd_reduce(G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var,
+                                        eps, nxt.relu, M, C)
+            if sp.gamma is not None:
+                grads[sp.gamma] = s2
+                grads[sp.beta] = s1
+            out = G if (own_g and ldg == C) else None
+            dY = ops.act_bwd_apply(G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var, eps,
+                                   nxt.relu, True, s1, s2, M, C, out=out, ldo=C)
+            ldy = C
+        elif sp.relu:
+            out = G if (own_g and ldg == C) else None
+            dY = ops.act_bwd_apply(G, ldg, nxt.raw, nxt.ld, None, None, None, None, 0.0, True,
+                                   False, None, None, M, C, out=out, ldo=C)
+            ldy = C
+        else:
+            dY, ldy = G, ldg
+        # weight gradient: dW[cout, cin] = dY^T [cout, M] * act(prev)[M, cin]
+        Wp = params[sp.w]
+        dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
+        grads[sp.w] = dW.view(Wp.shape)
+        if sp.b is not None:
+            grads[sp.b] = ops.colsum(dY, ldy, M, C)
+        if li > 0 or need_input_grad:
+            G = ops.gemm(dY, ldy, True, _w2d(Wp), sp.cin, False, M, sp.cin, sp.cout)
+            ldg = sp.cin
+            own_g = True
+        else:
+            G = None
+    return G
+
+
+class ChainFunction(torch.autograd.Function):
+    """autograd wrapper: y = chain(x) with the final activation materialised."""
+
+    @staticmethod
+    def forward(ctx, x, specs, training, *params):
+        x = x.contiguous()
+        M, K = x.shape
+        saved = [] if training else None  # eval-mode forwards keep nothing (no backward)
+        out = chain_forward(Deferred(x, K, K), M, specs, params, training, saved)
+        y = out.materialise(M)
+        ctx.specs, ctx.saved, ctx.M = specs, saved, M
+        ctx.nparams = len(params)
+        ctx.params = params
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if ctx.saved is None:
+            raise RuntimeError("backward through an eval-mode forward is not supported "
+                               "(the reference never does it: learning/main.py:229-311)")
+        gy = gy.contiguous()
+        grads = [None] * ctx.nparams
+        gx = chain_backward(gy, gy.shape[1], ctx.M, ctx.specs, ctx.params, ctx.saved,
+                            ctx.needs_input_grad[0], grads)
+        ctx.saved = None
+        return (gx, None, None) + tuple(grads)
+
+
+def run_sequential(seq, x, training):
+    """Runs an nn.Sequential of Linear/BN/ReLU through the fused chain with autograd support."""
+    specs, params = parse_sequential(seq, training)
+    return ChainFunction.apply(x, specs, training, *params)

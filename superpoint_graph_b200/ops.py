@@ -1,0 +1,392 @@
+"""Typed Python wrappers over the C-ABI (include/spg_b200.h).
+
+Every function takes CUDA tensors, validates shape/dtype/contiguity on the host and enqueues
+on torch's current stream.  CPU tensors are rejected: there is no CPU implementation in the
+product (the CPU restatement lives in oracle/ and is test infrastructure only).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+F32, F64 = 0, 1
+GRU_LAYERNORM, GRU_INGATE, GRU_BIAS = 1, 2, 4
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "superpoint_graph_b200 ops run on sm_100a CUDA tensors only (got a CPU tensor); "
+                "there is no CPU fallback")
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_workspaces = {}
+
+
+def workspace(nfloats, device):
+    """Per (device, stream) scratch buffer; stream order makes reuse across calls safe."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nfloats:
+        buf = torch.empty(max(int(nfloats), 1 << 16), dtype=torch.float32, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def zero_(t):
+    _need_cuda(t)
+    assert t.is_contiguous()
+    _lib.call("spg_zero", t, t.numel() * t.element_size(), _lib.current_stream())
+    return t
+
+
+# ------------------------------------------------------------------ graph structure
+class EccGraph(object):
+    """Device-side CSR views of one batched graph, shared by all ECC kernels.
+
+    Built on the host from the reference's `(idxn, idxe, degs)` triple
+    (ref: learning/ecc/GraphConvInfo.py:48-69): `tgt_rowptr` is the exclusive scan of the
+    in-degrees, `edge_tgt` the target of every edge, `(src_rowptr, src_perm)` a stable
+    source-sorted CSR used by the atomic-free grad_input kernel.
+    """
+
+    def __init__(self, idxn, idxe, degs, n_in=None):
+        idxn_np = idxn.detach().cpu().numpy().astype(np.int64, copy=False)
+        degs_np = degs.detach().cpu().numpy().astype(np.int64, copy=False)
+        self.n_out = int(degs_np.shape[0])
+        self.n_edges = int(idxn_np.shape[0])
+        if int(degs_np.sum()) != self.n_edges:
+            raise ValueError("sum(degs)=%d does not match the number of edges %d"
+                             % (int(degs_np.sum()), self.n_edges))
+        if n_in is None:
+            n_in = max(self.n_out, int(idxn_np.max()) + 1 if self.n_edges else 0)
+        self.n_in = int(n_in)
+        if self.n_edges and (idxn_np.min() < 0 or idxn_np.max() >= self.n_in):
+            raise ValueError("idxn out of range")
+        host = build_csr_host(idxn_np, degs_np, self.n_in)
+        self.host = host
+        self.idxe_host = None if idxe is None else idxe.detach().cpu().numpy().astype(np.int32)
+        self._dev = {}
+
+    def to(self, device):
+        device = torch.device(device)
+        key = (device.type, device.index)
+        if key not in self._dev:
+            d = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+            d["idxe"] = None if self.idxe_host is None else torch.from_numpy(self.idxe_host).to(device)
+            self._dev[key] = d
+        return self._dev[key]
+
+
+def build_csr_host(idxn, degs, n_in):
+    """Pure-numpy structure builder (also exercised by the CPU tests)."""
+    n_edges = idxn.shape[0]
+    tgt_rowptr = np.zeros(degs.shape[0] + 1, dtype=np.int64)
+    np.cumsum(degs, out=tgt_rowptr[1:])
+    edge_tgt = np.repeat(np.arange(degs.shape[0], dtype=np.int64), degs)
+    src_perm = np.argsort(idxn, kind="stable")
+    src_counts = np.bincount(idxn, minlength=n_in) if n_edges else np.zeros(n_in, dtype=np.int64)
+    src_rowptr = np.zeros(n_in + 1, dtype=np.int64)
+    np.cumsum(src_counts, out=src_rowptr[1:])
+    if n_edges >= 2 ** 31 or n_in >= 2 ** 31:
+        raise ValueError("graph too large for int32 indices")
+    return {
+        "tgt_rowptr": tgt_rowptr.astype(np.int32),
+        "idxn": idxn.astype(np.int32),
+        "edge_tgt": edge_tgt.astype(np.int32),
+        "src_rowptr": src_rowptr.astype(np.int32),
+        "src_perm": src_perm.astype(np.int32),
+    }
+
+
+# ------------------------------------------------------------------------------ ECC
+def ecc_fwd(x, w, graph, c_out, out=None):
+    _need_cuda(x, w)
+    x, w = _c(x), _c(w)
+    g = graph.to(x.device)
+    is_mat = int(w.dim() == 3)
+    c_in = x.shape[1]
+    if x.shape[0] != graph.n_in:
+        raise ValueError("input has %d rows, graph has %d nodes" % (x.shape[0], graph.n_in))
+    n_w = g["idxe"].max().item() + 1 if g["idxe"] is not None else graph.n_edges
+    if w.shape[0] < n_w:
+        raise ValueError("weights has %d rows, graph needs %d" % (w.shape[0], n_w))
+    if out is None:
+        out = torch.empty((graph.n_out, c_out), dtype=x.dtype, device=x.device)
+    _lib.call("spg_ecc_fwd", x, w, g["tgt_rowptr"], g["idxn"], g["idxe"], out, graph.n_out,
+              graph.n_edges, c_in, c_out, is_mat, _dt(x), _lib.current_stream())
+    return out
+
+
+def ecc_bwd_w(xs, gs, graph, w_shape, n_iter=1, out=None, accumulate=False):
+    """xs: [n_iter, n_in, c_in] (or [n_in, c_in]); gs: [n_iter, n_out, c_out]."""
+    _need_cuda(xs, gs)
+    xs, gs = _c(xs), _c(gs)
+    g = graph.to(xs.device)
+    is_mat = int(len(w_shape) == 3)
+    c_in, c_out = xs.shape[-1], gs.shape[-1]
+    if out is None:
+        if g["idxe"] is not None:
+            out = torch.zeros(w_shape, dtype=xs.dtype, device=xs.device)
+        else:
+            out = torch.empty(w_shape, dtype=xs.dtype, device=xs.device)
+    x_stride = xs.shape[-2] * c_in if xs.dim() == 3 else 0
+    g_stride = gs.shape[-2] * c_out if gs.dim() == 3 else 0
+    _lib.call("spg_ecc_bwd_w", xs, gs, x_stride, g_stride, n_iter, g["tgt_rowptr"], g["idxn"],
+              g["idxe"], g["edge_tgt"], out, graph.n_out, graph.n_edges, c_in, c_out, is_mat,
+              int(accumulate), _dt(xs), _lib.current_stream())
+    return out
+
+
+def ecc_bwd_x(w, g_out, graph, c_in, add0=None, add1=None):
+    _need_cuda(w, g_out, add0, add1)
+    w, g_out = _c(w), _c(g_out)
+    add0 = None if add0 is None else _c(add0)
+    add1 = None if add1 is None else _c(add1)
+    g = graph.to(w.device)
+    is_mat = int(w.dim() == 3)
+    c_out = g_out.shape[1]
+    gx = torch.empty((graph.n_in, c_in), dtype=w.dtype, device=w.device)
+    _lib.call("spg_ecc_bwd_x", w, g_out, g["tgt_rowptr"], g["src_rowptr"], g["src_perm"],
+              g["edge_tgt"], g["idxe"], add0, add1, gx, graph.n_in, graph.n_edges, c_in, c_out,
+              is_mat, _dt(w), _lib.current_stream())
+    return gx
+
+
+# ------------------------------------------------------------------------------ GRU
+def gru_fwd(x, h, w_ih, w_hh, b_ih, b_hh, w_ig, b_ig, flags, out=None):
+    _need_cuda(x, h, w_ih, w_hh)
+    x, h = _c(x), _c(h)
+    n, H = h.shape
+    assert x.shape == h.shape and w_ih.shape == (3 * H, H) and w_hh.shape == (3 * H, H)
+    if out is None:
+        out = torch.empty_like(h)
+    _lib.call("spg_gru_fwd", x, h, _c(w_ih), _c(w_hh), b_ih, b_hh,
+              None if w_ig is None else _c(w_ig), b_ig, out, n, H, flags, _lib.current_stream())
+    return out
+
+
+def gru_bwd(x, h, gy, w_ih, w_hh, b_ih, b_hh, w_ig, b_ig, flags, d_gi, d_gh, d_q, xprime, dpre,
+            d_x=None, d_h=None):
+    _need_cuda(x, h, gy)
+    x, h, gy = _c(x), _c(h), _c(gy)
+    n, H = h.shape
+    if d_x is None:
+        d_x = torch.empty_like(h)
+    if d_h is None:
+        d_h = torch.empty_like(h)
+    _lib.call("spg_gru_bwd", x, h, gy, _c(w_ih), _c(w_hh), b_ih, b_hh,
+              None if w_ig is None else _c(w_ig), b_ig, d_x, d_h, d_gi, d_gh, d_q, xprime, dpre,
+              n, H, flags, _lib.current_stream())
+    return d_x, d_h
+
+
+# ---------------------------------------------------------------------------- dense
+def _auto_split(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 63) // 64)
+    if tiles >= 148 or K < 1024:
+        return 1
+    split = min((2 * 148 + tiles - 1) // tiles, max(1, K // 256))
+    return max(1, split)
+
+
+def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=None,
+         a_aff=None, b_aff=None, split_k=None):
+    """C[M,N] = opA(A) opB(B) + bias.  a_aff/b_aff = (scale|None, shift|None, relu)."""
+    _need_cuda(A, B)
+    dev = A.device
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        ldc = N
+    elif ldc is None:
+        ldc = out.stride(0)
+    a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
+    b_s, b_t, b_r = b_aff if b_aff is not None else (None, None, False)
+    if split_k is None:
+        split_k = _auto_split(M, N, K)
+    ws = workspace(split_k * M * N, dev) if split_k > 1 else None
+    _lib.call("spg_gemm", A, lda, int(a_kmajor), B, ldb, int(b_kmajor), bias, out, ldc, M, N, K,
+              a_s, a_t, int(bool(a_r)), b_s, b_t, int(bool(b_r)), split_k, ws,
+              _lib.current_stream())
+    return out
+
+
+def _chunks(M):
+    return max(1, (M + 1023) // 1024)
+
+
+def colstats(Y, ldy, M, C):
+    _need_cuda(Y)
+    mean = torch.empty(C, dtype=torch.float32, device=Y.device)
+    var = torch.empty(C, dtype=torch.float32, device=Y.device)
+    ws = workspace(3 * C * _chunks(M), Y.device)
+    _lib.call("spg_colstats", Y, ldy, M, C, mean, var, ws, _lib.current_stream())
+    return mean, var
+
+
+def bn_fold(mean, var, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1, M=0,
+            num_batches_tracked=None):
+    _need_cuda(mean, var)
+    C = mean.numel()
+    scale = torch.empty(C, dtype=torch.float32, device=mean.device)
+    shift = torch.empty(C, dtype=torch.float32, device=mean.device)
+    _lib.call("spg_bn_fold", mean, var, gamma, beta, float(eps), scale, shift, running_mean,
+              running_var, num_batches_tracked, float(momentum), int(M), C, _lib.current_stream())
+    return scale, shift
+
+
+def affine_act(Y, ldy, M, C, scale=None, shift=None, relu=False, out=None, ldo=None):
+    _need_cuda(Y)
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float32, device=Y.device)
+        ldo = C
+    _lib.call("spg_affine_act", Y, ldy, scale, shift, int(bool(relu)), out, ldo, M, C,
+              _lib.current_stream())
+    return out
+
+
+def colsum(X, ldx, M, C):
+    _need_cuda(X)
+    out = torch.empty(C, dtype=torch.float32, device=X.device)
+    ws = workspace(C * _chunks(M), X.device)
+    _lib.call("spg_colsum", X, ldx, M, C, out, ws, _lib.current_stream())
+    return out
+
+
+def act_bwd_reduce(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, M, C):
+    _need_cuda(G, Y)
+    s1 = torch.empty(C, dtype=torch.float32, device=G.device)
+    s2 = torch.empty(C, dtype=torch.float32, device=G.device)
+    ws = workspace(2 * C * _chunks(M), G.device)
+    _lib.call("spg_act_bwd_reduce", G, ldg, Y, ldy, scale, shift, mean, var, float(eps),
+              int(bool(relu)), s1, s2, ws, M, C, _lib.current_stream())
+    return s1, s2
+
+
+def act_bwd_apply(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, has_bn, s1, s2, M, C,
+                  out=None, ldo=None):
+    _need_cuda(G)
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float32, device=G.device)
+        ldo = C
+    _lib.call("spg_act_bwd_apply", G, ldg, Y, ldy, scale, shift, mean, var, float(eps),
+              int(bool(relu)), int(bool(has_bn)), s1, s2, out, ldo, M, C, _lib.current_stream())
+    return out
+
+
+# ------------------------------------------------------------------------- PointNet
+def cloud_rows(clouds, T, ld, add_eye=False):
+    _need_cuda(clouds, T)
+    clouds = _c(clouds)
+    B, F, L = clouds.shape
+    rows = torch.empty((B * L, ld), dtype=torch.float32, device=clouds.device)
+    _lib.call("spg_cloud_rows", clouds, None if T is None else _c(T), int(bool(add_eye)), rows, ld,
+              B, F, L, _lib.current_stream())
+    return rows
+
+
+def segmax_fwd(Y, ldy, B, L, C, scale, shift, relu, pooled, ldp):
+    _need_cuda(Y, pooled)
+    argmax = torch.empty((B, C), dtype=torch.int32, device=Y.device)
+    _lib.call("spg_segmax_fwd", Y, ldy, scale, shift, int(bool(relu)), pooled, ldp, argmax, B, L, C,
+              _lib.current_stream())
+    return argmax
+
+
+def segmax_bwd(g_pooled, ldg, argmax, B, L, C):
+    _need_cuda(g_pooled, argmax)
+    G = torch.empty((B * L, C), dtype=torch.float32, device=g_pooled.device)
+    _lib.call("spg_segmax_bwd", g_pooled, ldg, argmax, G, C, B, L, C, _lib.current_stream())
+    return G
+
+
+def stn_apply_bwd(clouds, dXrows, ld):
+    _need_cuda(clouds, dXrows)
+    clouds = _c(clouds)
+    B, F, L = clouds.shape
+    dT = torch.empty((B, 4), dtype=torch.float32, device=clouds.device)
+    _lib.call("spg_stn_apply_bwd", clouds, dXrows, ld, dT, B, F, L, _lib.current_stream())
+    return dT
+
+
+def rows_scatter(src, idx, n_rows_out):
+    _need_cuda(src, idx)
+    src = _c(src)
+    n, C = src.shape
+    dst = torch.empty((n_rows_out, C), dtype=torch.float32, device=src.device)
+    zero_(dst)
+    _lib.call("spg_rows_scatter", src, idx, dst, n, C, _lib.current_stream())
+    return dst
+
+
+def rows_gather(src, idx):
+    _need_cuda(src, idx)
+    src = _c(src)
+    n = idx.numel()
+    C = src.shape[1]
+    dst = torch.empty((n, C), dtype=torch.float32, device=src.device)
+    _lib.call("spg_rows_gather", src, idx, dst, n, C, _lib.current_stream())
+    return dst
+
+
+# ----------------------------------------------------------------------------- step
+def ce_loss(logits, target, class_weight=None, ignore_index=-100, need_grad=True):
+    _need_cuda(logits, target, class_weight)
+    logits = _c(logits)
+    n, C = logits.shape
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    d_logits = torch.empty_like(logits) if need_grad else None
+    ws = torch.empty(2, dtype=torch.float64, device=logits.device)
+    _lib.call("spg_ce_loss", logits, _c(target), class_weight, int(ignore_index), loss, d_logits,
+              ws, n, C, _lib.current_stream())
+    return loss, d_logits
+
+
+def clamp_adam_(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                weight_decay=0.0, grad_clip=0.0, grad_scale=1.0):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    _lib.call("spg_clamp_adam", param, grad, exp_avg, exp_avg_sq, param.numel(), float(lr),
+              float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_clip),
+              float(grad_scale), int(step), _lib.current_stream())
+
+
+# ------------------------------------------------------------------------ profiling
+def prof_enable(on):
+    _lib.lib().spg_prof_enable(int(on))
+
+
+def prof_reset():
+    _lib.lib().spg_prof_reset()
+
+
+def prof_collect():
+    """Returns {kernel_name: (launches, total_ms)} for kernels launched since the last reset."""
+    import ctypes
+
+    L = _lib.lib()
+    L.spg_prof_collect()
+    out = {}
+    for k in range(L.spg_prof_num_kernels()):
+        n = ctypes.c_int64(0)
+        ms = ctypes.c_double(0.0)
+        L.spg_prof_kernel_stats(k, ctypes.byref(n), ctypes.byref(ms))
+        if n.value:
+            out[L.spg_prof_kernel_name(k).decode()] = (int(n.value), float(ms.value))
+    return out
+
+
+def total_launches():
+    return int(_lib.lib().spg_prof_total_launches())

@@ -1,0 +1,367 @@
+"""PointNet / STNkD / CloudEmbedder with the reference's operator signatures on top of the
+sm_100a kernels.
+
+Drop-in for `learning/pointnet.py` (ref: learning/pointnet.py:16-218): same class names,
+constructor arguments, attribute names (`stn`, `convs`, `fcs`, `proj`, `nfeat_stn`), parameter
+initialisation order (so `torch.manual_seed(0)` in `PointNet.__init__` yields the same initial
+weights) and state-dict keys.  The nn.Sequential containers only *hold* parameters and buffers;
+`forward` never calls them — it runs one hand-written forward/backward over the C-ABI
+(superpoint_graph_b200.dense + csrc/pointnet.cu).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .dense import Deferred, chain_backward, chain_forward, parse_sequential
+
+
+def _conv_stack(nfeat, widths, norm, n_group):
+    mods = []
+    for i, w in enumerate(widths):
+        mods.append(nn.Conv1d(widths[i - 1] if i > 0 else nfeat, w, 1))
+        if norm == 'batch':
+            mods.append(nn.BatchNorm1d(w))
+        elif norm == 'layer':
+            mods.append(nn.GroupNorm(1, w))
+        elif norm == 'group':
+            mods.append(nn.GroupNorm(n_group, w))
+        mods.append(nn.ReLU(True))
+    return nn.Sequential(*mods)
+
+
+def _round4(n):
+    return (n + 3) // 4 * 4
+
+
+class STNkD(nn.Module):
+    """Spatial transformer producing a KxK matrix per cloud (ref: learning/pointnet.py:16-61)."""
+
+    def __init__(self, nfeat, nf_conv, nf_fc, K=2, norm='batch', affine=True, n_group=1):
+        super(STNkD, self).__init__()
+        self.convs = _conv_stack(nfeat, nf_conv, norm, n_group)
+        mods = []
+        for i, w in enumerate(nf_fc):
+            mods.append(nn.Linear(nf_fc[i - 1] if i > 0 else nf_conv[-1], w))
+            if norm == 'batch':
+                mods.append(nn.BatchNorm1d(w))
+            elif norm == 'layer':
+                mods.append(nn.GroupNorm(1, w))
+            elif norm == 'group':
+                mods.append(nn.GroupNorm(n_group, w))
+            mods.append(nn.ReLU(True))
+        self.fcs = nn.Sequential(*mods)
+        self.proj = nn.Linear(nf_fc[-1], K * K)
+        nn.init.constant_(self.proj.weight, 0)
+        nn.init.constant_(self.proj.bias, 0)
+        self.eye = torch.eye(K).unsqueeze(0)
+        self._K = K
+        self._nfeat = nfeat
+
+    def forward(self, input):
+        """input [B, nfeat, L] -> [B, K, K] (= proj(...) + I)."""
+        if self.eye.device != input.device:
+            self.eye = self.eye.to(input.device)
+        T = _StnFunction.apply(input, self, self.training, *_stn_params(self, self.training)[1])
+        return T.view(-1, self._K, self._K) + self.eye
+
+
+def _stn_params(stn, training):
+    """(spec groups, flat parameter list) for convs | fcs+proj of an STNkD."""
+    cs, cp = parse_sequential(stn.convs, training)
+    fs, fp = parse_sequential(list(stn.fcs.children()) + [stn.proj], training)
+    off = len(cp)
+    for sp in fs:
+        sp.w += off
+        if sp.b is not None:
+            sp.b += off
+        if sp.gamma is not None:
+            sp.gamma += off
+            sp.beta += off
+    return (cs, fs), cp + fp
+
+
+def _stn_forward(rows, ld, B, L, groups, params, training, saved):
+    """rows: raw point rows [B*L, ld]; returns flat T [B, K*K] (without the identity)."""
+    cs, fs = groups
+    M = B * L
+    nfeat = cs[0].cin
+    sv_c = [] if saved is not None else None
+    out = chain_forward(Deferred(rows, ld, nfeat), M, cs, params, training, sv_c)
+    Cs = out.C
+    pooled = torch.empty((B, Cs), dtype=torch.float32, device=rows.device)
+    argmax = ops.segmax_fwd(out.raw, out.ld, B, L, Cs, out.scale, out.shift, out.relu, pooled, Cs)
+    sv_f = [] if saved is not None else None
+    t = chain_forward(Deferred(pooled, Cs, Cs), B, fs, params, training, sv_f)
+    T = t.materialise(B)
+    if saved is not None:
+        saved.update(stn_c=sv_c, stn_f=sv_f, stn_argmax=argmax, stn_Cs=Cs)
+    return T
+
+
+def _stn_backward(dT, B, L, groups, params, saved, grads):
+    cs, fs = groups
+    Cs = saved["stn_Cs"]
+    g_pool = chain_backward(dT, dT.shape[1], B, fs, params, saved["stn_f"], True, grads)
+    G = ops.segmax_bwd(g_pool, Cs, saved["stn_argmax"], B, L, Cs)
+    chain_backward(G, Cs, B * L, cs, params, saved["stn_c"], False, grads, own_g=True)
+
+
+class _StnFunction(torch.autograd.Function):
+    """Stand-alone STN (used by STNkD.forward and LocalCloudEmbedder)."""
+
+    @staticmethod
+    def forward(ctx, clouds, stn, training, *params):
+        clouds = clouds.contiguous()
+        B, F, L = clouds.shape
+        groups, _ = _stn_params(stn, training)
+        ld = _round4(F)
+        rows = ops.cloud_rows(clouds, None, ld)
+        saved = {} if training else None
+        T = _stn_forward(rows, ld, B, L, groups, params, training, saved)
+        ctx.saved, ctx.groups, ctx.params, ctx.dims = saved, groups, params, (B, L)
+        return T
+
+    @staticmethod
+    def backward(ctx, dT):
+        if ctx.saved is None:
+            raise RuntimeError("backward through an eval-mode forward is not supported")
+        grads = [None] * len(ctx.params)
+        B, L = ctx.dims
+        _stn_backward(dT.contiguous(), B, L, ctx.groups, ctx.params, ctx.saved, grads)
+        ctx.saved = None
+        return (None, None, None) + tuple(grads)
+
+
+class PointNet(nn.Module):
+    """PointNet with one spatial transformer and a "global" input concatenated after the max-pool
+    (ref: learning/pointnet.py:63-133)."""
+
+    def __init__(self, nf_conv, nf_fc, nf_conv_stn, nf_fc_stn, nfeat, nfeat_stn=2, nfeat_global=1,
+                 prelast_do=0.5, last_ac=False, is_res=False, norm='batch', affine=True, n_group=1,
+                 last_bn=False):
+        super(PointNet, self).__init__()
+        torch.manual_seed(0)  # ref: learning/pointnet.py:78 (part of the observable behaviour)
+        if nfeat_stn > 0:
+            self.stn = STNkD(nfeat_stn, nf_conv_stn, nf_fc_stn, norm=norm, n_group=n_group)
+        self.nfeat_stn = nfeat_stn
+        self.convs = _conv_stack(nfeat, nf_conv, norm, n_group)
+        mods = []
+        for i, w in enumerate(nf_fc):
+            mods.append(nn.Linear(nf_fc[i - 1] if i > 0 else nf_conv[-1] + nfeat_global, w))
+            if i < len(nf_fc) - 1 or last_ac:
+                if norm == 'batch':
+                    mods.append(nn.BatchNorm1d(w))
+                elif norm == 'layer':
+                    mods.append(nn.GroupNorm(1, w))
+                elif norm == 'group':
+                    mods.append(nn.GroupNorm(n_group, w))
+                mods.append(nn.ReLU(True))
+            if i == len(nf_fc) - 2 and prelast_do > 0:
+                mods.append(nn.Dropout(prelast_do))
+        if is_res:
+            nn.init.normal_(mods[-1].weight, mean=0, std=1e-2)
+            nn.init.normal_(mods[-1].bias, mean=0, std=1e-2)
+        self.fcs = nn.Sequential(*mods)
+        self._nfeat = nfeat
+        self._nfeat_global = nfeat_global
+
+    def _groups(self, training):
+        """Spec groups and the flat parameter list: [stn convs | stn fcs+proj | convs | fcs]."""
+        params = []
+        stn_groups = None
+        if self.nfeat_stn > 0:
+            stn_groups, params = _stn_params(self.stn, training)
+            params = list(params)
+        groups = []
+        for seq in (self.convs, self.fcs):
+            sp, pp = parse_sequential(seq, training)
+            off = len(params)
+            for s in sp:
+                s.w += off
+                if s.b is not None:
+                    s.b += off
+                if s.gamma is not None:
+                    s.gamma += off
+                    s.beta += off
+            params += pp
+            groups.append(sp)
+        return stn_groups, groups[0], groups[1], params
+
+    def forward(self, input, input_global):
+        """input [B, nfeat, L], input_global [B] | [B, G] | None -> [B, nf_fc[-1]]."""
+        training = self.training
+        stn_g, conv_g, fc_g, params = self._groups(training)
+        if input_global is not None:
+            input_global = input_global.reshape(input.shape[0], -1).float()
+        if not training and input.shape[0] > _EVAL_CHUNK:
+            outs = []
+            for i in range(0, input.shape[0], _EVAL_CHUNK):
+                gl = None if input_global is None else input_global[i:i + _EVAL_CHUNK]
+                outs.append(_PointNetFunction.apply(input[i:i + _EVAL_CHUNK], gl, self.nfeat_stn,
+                                                    (stn_g, conv_g, fc_g), training, *params))
+            return torch.cat(outs, 0)
+        return _PointNetFunction.apply(input, input_global, self.nfeat_stn, (stn_g, conv_g, fc_g),
+                                       training, *params)
+
+
+_EVAL_CHUNK = 16384  # clouds per eval-mode slice (bounds the [B*L, 256] activation to 2 GB)
+
+
+class _PointNetFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, clouds, glob, nfeat_stn, groups, training, *params):
+        stn_g, conv_g, fc_g = groups
+        clouds = clouds.contiguous()
+        if clouds.dtype != torch.float32:
+            raise TypeError("PointNet kernels are float32")
+        B, F, L = clouds.shape
+        M = B * L
+        ld = _round4(F)
+        saved = {} if training else None
+        T = None
+        if nfeat_stn > 0:
+            rows0 = ops.cloud_rows(clouds, None, ld)
+            T = _stn_forward(rows0, ld, B, L, stn_g, params, training, saved)
+            rows = ops.cloud_rows(clouds, T, ld, add_eye=True)
+            del rows0
+        else:
+            rows = ops.cloud_rows(clouds, None, ld)
+        sv_c = [] if training else None
+        out = chain_forward(Deferred(rows, ld, F), M, conv_g, params, training, sv_c)
+        Ct = out.C
+        G = 0 if glob is None else glob.shape[1]
+        ldp = _round4(Ct + G)
+        pooled = torch.empty((B, ldp), dtype=torch.float32, device=clouds.device)
+        argmax = ops.segmax_fwd(out.raw, out.ld, B, L, Ct, out.scale, out.shift, out.relu, pooled,
+                                ldp)
+        if G > 0:
+            glob = glob.contiguous()
+            ops.affine_act(glob, G, B, G, out=pooled[:, Ct:], ldo=ldp)
+        sv_f = [] if training else None
+        y = chain_forward(Deferred(pooled, ldp, Ct + G), B, fc_g, params, training, sv_f)
+        res = y.materialise(B)
+        if training:
+            saved.update(conv=sv_c, fc=sv_f, argmax=argmax, Ct=Ct, G=G, ld=ld)
+        ctx.saved, ctx.groups, ctx.params = saved, groups, params
+        ctx.dims = (B, F, L, nfeat_stn)
+        ctx.clouds = clouds if (training and nfeat_stn > 0) else None
+        return res
+
+    @staticmethod
+    def backward(ctx, gy):
+        if ctx.saved is None:
+            raise RuntimeError("backward through an eval-mode forward is not supported "
+                               "(the reference never does it: learning/main.py:229-311)")
+        stn_g, conv_g, fc_g = ctx.groups
+        params, saved = ctx.params, ctx.saved
+        B, F, L, nfeat_stn = ctx.dims
+        grads = [None] * len(params)
+        gy = gy.contiguous()
+        Ct, ld = saved["Ct"], saved["ld"]
+        g_pool = chain_backward(gy, gy.shape[1], B, fc_g, params, saved["fc"], True, grads)
+        Gt = ops.segmax_bwd(g_pool, g_pool.shape[1], saved["argmax"], B, L, Ct)
+        del g_pool
+        g_rows = chain_backward(Gt, Ct, B * L, conv_g, params, saved["conv"], nfeat_stn > 0, grads,
+                                own_g=True)
+        if nfeat_stn > 0:
+            dT = ops.stn_apply_bwd(ctx.clouds, g_rows, g_rows.shape[1])
+            del g_rows
+            _stn_backward(dT, B, L, stn_g, params, saved, grads)
+        ctx.saved = None
+        ctx.clouds = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class CloudEmbedder():
+    """Evaluates PointNet on the superpoints that have a cloud and scatters the result into
+    zero-filled descriptors (ref: learning/pointnet.py:138-180)."""
+
+    def __init__(self, args):
+        self.args = args
+        self.bw_hook = lambda: None
+        self.run = self.run_full_monger if args.ptn_mem_monger else self.run_full
+
+    def _prep(self, clouds_flag, clouds, clouds_global):
+        idx_valid = torch.nonzero(clouds_flag.eq(0)).reshape(-1)
+        if not self.args.cuda:
+            raise RuntimeError("superpoint_graph_b200 runs on CUDA only (args.cuda must be 1)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        return (clouds.to(dev, non_blocking=True), clouds_global.to(dev, non_blocking=True),
+                idx_valid.to(dev, non_blocking=True))
+
+    def run_full(self, model, clouds_meta, clouds_flag, clouds, clouds_global):
+        clouds, clouds_global, idx_valid = self._prep(clouds_flag, clouds, clouds_global)
+        out = model.ptn(clouds, clouds_global)
+        return _ScatterRows.apply(out, idx_valid, clouds_flag.size(0))
+
+    def run_full_monger(self, model, clouds_meta, clouds_flag, clouds, clouds_global):
+        """Memory mongering (ref: learning/pointnet.py:160-180): forward without saving, full
+        recomputation in `bw_hook`."""
+        clouds, clouds_global, idx_valid = self._prep(clouds_flag, clouds, clouds_global)
+        was_training = model.training
+        with torch.no_grad():
+            if was_training:
+                # batch statistics are needed but nothing is kept; running stats must only be
+                # updated once per step, which the recomputation in bw_hook does.
+                out = _forward_no_stat_update(model.ptn, clouds, clouds_global)
+            else:
+                out = model.ptn(clouds, clouds_global)
+        out = out.detach().requires_grad_(was_training)
+
+        def bw_hook():
+            out_v2 = model.ptn(clouds, clouds_global)
+            out_v2.backward(out.grad)
+
+        self.bw_hook = bw_hook
+        return _ScatterRows.apply(out, idx_valid, clouds_flag.size(0))
+
+
+def _forward_no_stat_update(ptn, clouds, clouds_global):
+    """Training-mode forward whose BatchNorm running statistics are restored afterwards.
+
+    The reference's monger path updates running stats twice per step (no_grad forward +
+    recomputation, ref: learning/pointnet.py:166-174); to stay bit-compatible with that observable
+    behaviour we simply run the normal training forward, i.e. we also update twice."""
+    return ptn(clouds, clouds_global)
+
+
+class _ScatterRows(torch.autograd.Function):
+    """descriptors = zeros[N, C]; descriptors[idx] = out (ref: learning/pointnet.py:156-157)."""
+
+    @staticmethod
+    def forward(ctx, out, idx, n_rows):
+        ctx.save_for_backward(idx)
+        return ops.rows_scatter(out, idx, n_rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return ops.rows_gather(g.contiguous(), idx), None, None
+
+
+class LocalCloudEmbedder():
+    """Learned-partition embedder: external STN, xy transform, tiny PointNet, L2 normalisation
+    (ref: learning/pointnet.py:182-218).  Signature kept; the PointNet/STN run on the fused path,
+    the 65535-cloud chunking of the reference (a cuDNN limit) is unnecessary here."""
+
+    def __init__(self, args):
+        self.nfeat_stn = args.ptn_nfeat_stn
+        self.stn_as_global = args.stn_as_global
+
+    def run_batch(self, model, clouds, clouds_global, *excess):
+        if self.nfeat_stn > 0:
+            T = model.stn(clouds[:, :self.nfeat_stn, :])
+            xy_transf = torch.bmm(clouds[:, :2, :].transpose(1, 2), T).transpose(1, 2)
+            clouds = torch.cat([xy_transf, clouds[:, 2:, :]], 1)
+            if self.stn_as_global:
+                clouds_global = torch.cat([clouds_global, T.view(-1, 4)], 1)
+        out = model.ptn(clouds, clouds_global)
+        return nn.functional.normalize(out)
+
+    def run_batch_cpu(self, model, clouds, clouds_global, *excess):
+        batch_size = 2 ** 10 - 1
+        outs = []
+        for i in range(0, clouds.shape[0], batch_size):
+            outs.append(self.run_batch(model, clouds[i:i + batch_size], clouds_global[i:i + batch_size]).cpu())
+        return torch.cat(outs)
