@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""SPG train-step benchmark (BASELINE.json: "SPG train-step edges+points/sec ...; ECC scatter HBM %peak").
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W   # the reference's CPU algorithm (oracle port)
+
+A "step" is one full training step of configs[1] ("S3DIS Area-5 fold training, gru_10_1_1_1_0,
+fp32") on one synthetic S3DIS-shaped batch per GPU: PointNet embedding of every superpoint that has
+a cloud, filter network, 10 x {ECC, GRUCellEx}, classifier, weighted CE, full backward,
+element-wise gradient clamp, Adam (learning/main.py:199-213).  value = (edges + points) per second
+summed over ranks (weak scaling: one batch of scenes per rank, one NCCL all-reduce of the flat
+gradient per step).
+
+Timing: every step is bracketed by CUDA events on the launching stream; an L2 flush (a 256 MiB
+memset) runs between steps outside the brackets; the reported time is the max over ranks of the
+summed step times, after a barrier + synchronize on both sides of the K steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "spg_train_step_edges_plus_points_per_sec"
+UNIT = "edges+points/s"
+PCFG = dict(n_conv=5, n_fc=3, n_conv_stn=3, n_fc_stn=2, nfeat_stn=14)
+MCFG = dict(fnet_widths=[13, 32, 128, 64, 32], bnidx=2, nrepeats=10, layernorm=True, ingate=True,
+            cat_all=False)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nodes", type=int, default=1024, help="superpoints per batch (2 scenes x 512)")
+    ap.add_argument("--ecc-nodes", type=int, default=100000, help="ECC roofline microbench size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def workload_counts(batch):
+    from superpoint_graph_b200.synthetic import batch_counts
+    N, nv, pts, E = batch_counts(batch)
+    return dict(superpoints=N, embedded_superpoints=nv, points=pts, edges=E)
+
+
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, "/tmp/spg_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                mx = float(f[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU algorithm (oracle port of learning/main.py:199-213 with the per-node
+    Python loops of GraphConvModule.py:82-88,114-121) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import nets_ref
+    from superpoint_graph_b200.synthetic import make_batch
+    from superpoint_graph_b200.trainer import create_model, make_args
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    batch = make_batch(n_nodes=args.nodes, seed=1)
+    counts = workload_counts(batch)
+    margs = make_args()
+    model = create_model(margs)
+    sd_ecc = {k: v.clone() for k, v in model.ecc.state_dict().items()}
+    sd_ptn = {k: v.clone() for k, v in model.ptn.state_dict().items()}
+    tr = nets_ref.RefTrainer(sd_ptn, sd_ecc, PCFG, MCFG, lr=margs.lr, grad_clip=margs.grad_clip, ecc_mode="loop")
+    for _ in range(args.warmup):
+        tr.step(batch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(batch)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = (counts["edges"] + counts["points"]) / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload="S3DIS-shaped training step, gru_10_1_1_1_0,f_13, fp32", **counts),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d full training steps of the same batch (oracle/nets_ref.RefTrainer, "
+                                   "ecc_mode=loop)" % args.steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def cpu_baseline(batch, counts, margs, sd_ptn, sd_ecc, budget_s=25.0):
+    from oracle import nets_ref
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    out = {}
+    for mode in ("loop", "vec"):
+        tr = nets_ref.RefTrainer(sd_ptn, sd_ecc, PCFG, MCFG, lr=margs.lr, grad_clip=margs.grad_clip, ecc_mode=mode)
+        tr.step(batch)  # warm-up
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < 5 and (time.perf_counter() - t_start) < budget_s / 2:
+            t0 = time.perf_counter()
+            tr.step(batch)
+            times.append(time.perf_counter() - t0)
+        times.sort()
+        out[mode] = (times[len(times) // 2], len(times))
+    dt, n = out["loop"]
+    return {"value": (counts["edges"] + counts["points"]) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "median of %d full training steps of the same batch on the host (oracle port of the "
+                      "reference CPU path incl. its per-node Python loops)" % n,
+            "ms_per_step": dt * 1e3,
+            "vectorized_ms_per_step": out["vec"][0] * 1e3}
+
+
+def ecc_roofline(dev, n_nodes, pk):
+    """ECC gather-product-scatter kernels at sweep size (configs[4]: 100k superpoints, ~1M edges;
+    filter banks far larger than L2).  Algorithmic bytes per SURVEY.md §8(d)."""
+    from superpoint_graph_b200 import ops
+    from superpoint_graph_b200.synthetic import make_batch
+    b = make_batch(n_nodes=n_nodes, seed=5)
+    N, E, H = b["degs"].numel(), b["idxn"].numel(), 32
+    graph = ops.EccGraph(b["idxn"], None, b["degs"], n_in=N)
+    x = torch.randn(N, H, device=dev)
+    g = torch.randn(N, H, device=dev)
+    res = {}
+    for mode in ("vv", "mat"):
+        w = torch.randn((E, H, H) if mode == "mat" else (E, H), device=dev)
+        wbytes = 4 * H * H * E if mode == "mat" else 4 * H * E
+        cases = {
+            "fwd": (lambda: ops.ecc_fwd(x, w, graph, H), wbytes + 8 * H * N + 4 * E + 4 * (N + 1)),
+            "bwd_x": (lambda: ops.ecc_bwd_x(w, g, graph, H), wbytes + 8 * H * N + 8 * E + 8 * (N + 1)),
+        }
+        gw = torch.empty_like(w)
+        cases["bwd_w"] = (lambda: ops.ecc_bwd_w(x, g, graph, tuple(w.shape), out=gw), wbytes + 8 * H * N + 4 * E + 4 * (N + 1))
+        for name, (fn, nbytes) in cases.items():
+            for _ in range(3):
+                fn()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for s, e in ev:
+                s.record()
+                fn()
+                e.record()
+            torch.cuda.synchronize()
+            ms = sorted(s.elapsed_time(e) for s, e in ev)[len(ev) // 2]
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res["%s_%s" % (mode, name)] = {"ms": ms, "bytes": nbytes, "gbs": gbs, "frac": gbs / pk["hbm"]}
+        del w, gw
+    return dict(nodes=N, edges=E, kernels=res)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    from superpoint_graph_b200 import _lib, ops
+    from superpoint_graph_b200.synthetic import make_batch
+    from superpoint_graph_b200.trainer import HostBatch, Trainer, create_model, make_args
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    _lib.lib()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    pk = peaks()
+
+    margs = make_args()
+    model = create_model(margs)  # PointNet reseeds torch to 0: identical replicas on every rank
+    sd_ecc = {k: v.clone() for k, v in model.ecc.state_dict().items()}
+    sd_ptn = {k: v.clone() for k, v in model.ptn.state_dict().items()}
+    model.to(dev)
+    trainer = Trainer(model, margs, process_group=pg, world_size=world)
+
+    # 4 distinct batches per rank, rotated; rank-offset seeds (scene-parallel)
+    batches = [make_batch(n_nodes=args.nodes, seed=1 + 1000 * rank + i) for i in range(4)]
+    hbs = [HostBatch(b) for b in batches]
+    counts = workload_counts(batches[0])
+    units = [workload_counts(b)["edges"] + workload_counts(b)["points"] for b in batches]
+    dbs = [hb.to_device(dev) for hb in hbs]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for i in range(args.warmup):
+        trainer.train_step(dbs[i % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ops.total_launches()
+    evs = []
+    done_units = 0
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush, outside the event bracket
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        trainer.train_step(dbs[i % 4])
+        e.record()
+        evs.append((s, e))
+        done_units += units[i % 4]
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = ops.total_launches() - launches0
+    total_ms = sum(s.elapsed_time(e) for s, e in evs)
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    uu = torch.tensor([float(done_units)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+    total_ms, all_units = float(tt), float(uu)
+    value = all_units / (total_ms * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers (H2D + step + D2H of loss/logits)
+    h2d = hbs[0].h2d_bytes()
+    out_host = torch.empty((args.nodes, margs.classes), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    for i in range(max(3, args.warmup // 2)):
+        db = hbs[i % 4].to_device(dev)
+        trainer.train_step(db)
+    barrier()
+    e2e_ms, e2e_units = 0.0, 0
+    for i in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        db = hbs[i % 4].to_device(dev)
+        loss, logits = trainer.train_step(db)
+        out_host[:logits.shape[0]].copy_(logits, non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)
+        e.record()
+        e.synchronize()  # the trainer reads loss/logits on the host every step (main.py:216-221)
+        e2e_ms += s.elapsed_time(e)
+        e2e_units += units[i % 4]
+    barrier()
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    u2 = torch.tensor([float(e2e_units)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u2, op=dist.ReduceOp.SUM)
+    e2e_value = float(u2) / (float(t2) * 1e-3)
+    d2h = int(args.nodes * margs.classes * 4 + 4)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload="configs[1]: S3DIS-shaped training step, gru_10_1_1_1_0,f_13, fp32, "
+                                "2 scenes x %d superpoints per GPU" % (args.nodes // 2),
+                       parallelism="scene-parallel dp%d, one NCCL all-reduce of the flat gradient per step" % world,
+                       l2="256 MiB memset between timed steps (outside the event brackets); 4 rotating batches",
+                       **counts),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(t2) / args.steps},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
+        "clocks": clocks,
+        "peaks": pk["source"],
+    }
+
+    if rank == 0 and not args.no_roofline:
+        # per-kernel shares of the step (events around every launch; separate, untimed pass)
+        ops.prof_reset()
+        ops.prof_enable(1)
+        flops0 = ops.GEMM_FLOPS[0]
+        nprof = 3
+        for i in range(nprof):
+            trainer.train_step(dbs[i % 4]) if world == 1 else None
+        torch.cuda.synchronize()
+        ops.prof_enable(0)
+        if world == 1:
+            ks = ops.prof_collect()
+            tot = sum(v[1] for v in ks.values())
+            top = sorted(ks.items(), key=lambda kv: -kv[1][1])
+            line["kernel_shares"] = {k: {"launches_per_step": v[0] / nprof, "ms_per_step": v[1] / nprof,
+                                         "share": v[1] / tot} for k, v in top[:10]}
+            gname, (gl, gms) = top[0]
+            if gname == "gemm_f32":
+                flops = (ops.GEMM_FLOPS[0] - flops0)
+                ach = flops / (gms * 1e-3) / 1e12
+                line["roofline"] = {"kernel": gname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
+                                    "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                                    "note": "exact-fp32 FMA GEMM (SIMT) measured against the bf16 tensor peak"}
+        try:
+            er = ecc_roofline(dev, args.ecc_nodes, pk)
+            line["roofline_ecc"] = er
+            k = er["kernels"]["mat_fwd"]
+            ecc_obj = {"kernel": "ecc_mat_fwd", "bound": "hbm", "achieved": k["gbs"], "peak": pk["hbm"],
+                       "unit": "GB/s", "frac": k["frac"], "traffic": None,
+                       "workload": "configs[4]-scale: %d superpoints, %d edges, [E,32,32] filters" % (er["nodes"], er["edges"])}
+            if "roofline" not in line:
+                line["roofline"] = ecc_obj
+            else:
+                line["roofline_ecc_scatter"] = ecc_obj
+        except Exception as ex:  # keep the bench line even if the microbench cannot run
+            line["roofline_ecc_error"] = repr(ex)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(batches[0], counts, margs, sd_ptn, sd_ecc)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

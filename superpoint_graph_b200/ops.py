@@ -195,6 +195,9 @@ def gru_bwd(x, h, gy, w_ih, w_hh, b_ih, b_hh, w_ig, b_ig, flags, d_gi, d_gh, d_q
 
 
 # ---------------------------------------------------------------------------- dense
+GEMM_FLOPS = [0]  # algorithmic FLOPs (2*M*N*K) issued through gemm(); read by bench.py
+
+
 def _auto_split(M, N, K):
     tiles = ((M + 127) // 128) * ((N + 63) // 64)
     if tiles >= 148 or K < 1024:
@@ -215,6 +218,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
         ldc = out.stride(0)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
     b_s, b_t, b_r = b_aff if b_aff is not None else (None, None, False)
+    GEMM_FLOPS[0] += 2 * M * N * K
     if split_k is None:
         split_k = _auto_split(M, N, K)
     ws = workspace(split_k * M * N, dev) if split_k > 1 else None

@@ -28,7 +28,7 @@ def _knn_edges(rng, n, k):
     return pairs[pairs[:, 0] != pairs[:, 1]]
 
 
-def make_batch(n_nodes=2048, k=7, nfeat=14, npts=128, n_edge_feats=13, n_classes=13, minpts=40,
+def make_batch(n_nodes=2048, k=8, nfeat=14, npts=128, n_edge_feats=13, n_classes=13, minpts=40,
                seed=1, isolated_frac=0.01):
     """Returns a dict of CPU torch tensors:
     clouds [Nv,F,L] f32, clouds_global [Nv] f32, clouds_flag [N] int64 (0 | -1),

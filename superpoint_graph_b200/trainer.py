@@ -1,0 +1,155 @@
+"""The training / inference step of the reference's trainer on the sm_100a path.
+
+What `learning/main.py:189-221` does per batch — set_info, zero_grad, PointNet embedding, graph
+network, weighted cross entropy, backward, element-wise gradient clamp, Adam, logits to the host —
+with the model's parameters living in ONE flat fp32 buffer so that the gradient all-reduce is a
+single NCCL call and clamp+Adam a single kernel (scene-parallel data parallelism: every rank
+owns whole scenes, the graph never crosses devices).
+"""
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .spg_ecc import GraphConvInfo
+from .spg_graphnet import GraphNetwork
+from .spg_pointnet import CloudEmbedder, PointNet
+
+S3DIS_ARGS = dict(
+    model_config="gru_10_1_1_1_0,f_13", ptn_widths=[[64, 64, 128, 128, 256], [256, 64, 32]],
+    ptn_widths_stn=[[64, 64, 128], [128, 64]], ptn_nfeat_stn=14, ptn_prelast_do=0,
+    ptn_mem_monger=0, fnet_widths=[32, 128, 64], fnet_llbias=0, fnet_orthoinit=1, fnet_bnidx=2,
+    edge_mem_limit=30000, node_feats=14, edge_feats=13, classes=13, lr=1e-2, grad_clip=1.0,
+    wd=0.0, cuda=1, use_pyg=0)
+
+
+def make_args(**overrides):
+    d = dict(S3DIS_ARGS)
+    d.update(overrides)
+    return SimpleNamespace(**d)
+
+
+def create_model(args):
+    """ref: learning/main.py:414-431 (`model.ecc` is registered before `model.ptn`)."""
+    model = nn.Module()
+    nfeat = args.ptn_widths[1][-1]
+    model.ecc = GraphNetwork(args.model_config, nfeat, [args.edge_feats] + args.fnet_widths,
+                             args.fnet_orthoinit, args.fnet_llbias, args.fnet_bnidx,
+                             args.edge_mem_limit, use_pyg=args.use_pyg, cuda=args.cuda)
+    model.ptn = PointNet(args.ptn_widths[0], args.ptn_widths[1], args.ptn_widths_stn[0],
+                         args.ptn_widths_stn[1], args.node_feats, args.ptn_nfeat_stn,
+                         prelast_do=args.ptn_prelast_do)
+    return model
+
+
+def flatten_parameters(model):
+    """Moves every parameter into one contiguous fp32 buffer (parameters become views)."""
+    params = [p for p in model.parameters()]
+    total = sum(p.numel() for p in params)
+    flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        off += n
+    return flat, params
+
+
+class HostBatch(object):
+    """One collated batch in pinned host memory, in the layout the reference's collate produces
+    (learning/spg.py:178-193) plus the host-built CSR views of the graph."""
+
+    FIELDS = ("clouds", "clouds_global", "edgefeats", "labels", "idx_valid")
+
+    def __init__(self, batch):
+        self.n_nodes = int(batch["degs"].numel())
+        flag = batch["clouds_flag"]
+        self.idx_valid = torch.nonzero(flag.eq(0)).reshape(-1)
+        self.clouds = batch["clouds"]
+        self.clouds_global = batch["clouds_global"]
+        self.edgefeats = batch["edgefeats"]
+        self.labels = batch["labels"]
+        self.gi = GraphConvInfo.from_arrays(batch["idxn"], batch["degs"], batch["edgefeats"])
+        self.graph_host = self.gi.graph().host
+        if torch.cuda.is_available():
+            for f in self.FIELDS:
+                setattr(self, f, getattr(self, f).pin_memory())
+            self.graph_pinned = {k: torch.from_numpy(v).pin_memory() for k, v in self.graph_host.items()}
+        else:
+            self.graph_pinned = {k: torch.from_numpy(v) for k, v in self.graph_host.items()}
+
+    def h2d_bytes(self):
+        n = sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
+        n += sum(v.numel() * v.element_size() for v in self.graph_pinned.values())
+        return int(n)
+
+    def to_device(self, device):
+        """Asynchronous copies on the current stream; returns a DeviceBatch."""
+        d = DeviceBatch()
+        for f in self.FIELDS:
+            setattr(d, f, getattr(self, f).to(device, non_blocking=True))
+        g = self.gi.graph()
+        key = (device.type, device.index)
+        dev = {k: v.to(device, non_blocking=True) for k, v in self.graph_pinned.items()}
+        dev["idxe"] = None
+        g._dev[key] = dev  # the kernels read the graph through EccGraph.to(device)
+        d.gi = self.gi
+        d.gi._edgefeats = d.edgefeats
+        d.n_nodes = self.n_nodes
+        return d
+
+
+class DeviceBatch(object):
+    pass
+
+
+class Trainer(object):
+    """zero_grad / forward / loss / backward / (all-reduce) / clamp / Adam, as one object."""
+
+    def __init__(self, model, args, class_weights=None, process_group=None, world_size=1):
+        self.model, self.args = model, args
+        self.flat, self.params = flatten_parameters(model)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = 0
+        self.class_weights = class_weights
+        self.pg, self.world_size = process_group, world_size
+        self.embedder = CloudEmbedder(SimpleNamespace(cuda=1, ptn_mem_monger=args.ptn_mem_monger))
+
+    def forward(self, db):
+        self.model.ecc.gconvs[0].set_info(db.gi)
+        out = self.model.ptn(db.clouds, db.clouds_global)
+        emb = _scatter(out, db.idx_valid, db.n_nodes)
+        return self.model.ecc(emb)
+
+    def train_step(self, db):
+        """One optimisation step on a device-resident batch; returns (loss[1], logits)."""
+        self.model.train()
+        for p in self.params:
+            p.grad = None
+        logits = self.forward(db)
+        loss, d_logits = ops.ce_loss(logits, db.labels, self.class_weights, -100)
+        logits.backward(d_logits)
+        self.embedder.bw_hook()
+        torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_grad)
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        self.step_count += 1
+        ops.clamp_adam_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                        lr=self.args.lr, weight_decay=self.args.wd, grad_clip=self.args.grad_clip,
+                        grad_scale=1.0 / self.world_size)
+        return loss, logits.detach()
+
+    @torch.no_grad()
+    def eval_step(self, db):
+        self.model.eval()
+        return self.forward(db)
+
+
+def _scatter(out, idx_valid, n_nodes):
+    from .spg_pointnet import _ScatterRows
+
+    return _ScatterRows.apply(out, idx_valid, n_nodes)
