@@ -249,7 +249,8 @@ def run_b200(args):
     pk = peaks()
 
     margs = make_args()
-    model = create_model(margs)  # PointNet reseeds torch to 0: identical replicas on every rank
+    torch.manual_seed(1)  # --seed 1 (main.py:77); Trainer also broadcasts rank 0's parameters once
+    model = create_model(margs)
     sd_ecc = {k: v.clone() for k, v in model.ecc.state_dict().items()}
     sd_ptn = {k: v.clone() for k, v in model.ptn.state_dict().items()}
     model.to(dev)

@@ -117,6 +117,8 @@ class Trainer(object):
         self.step_count = 0
         self.class_weights = class_weights
         self.pg, self.world_size = process_group, world_size
+        if world_size > 1:  # one-time setup collective: guarantee identical replicas
+            torch.distributed.broadcast(self.flat, 0, group=process_group)
         self.embedder = CloudEmbedder(SimpleNamespace(cuda=1, ptn_mem_monger=args.ptn_mem_monger))
 
     def forward(self, db):
