@@ -133,8 +133,14 @@ int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const floa
 int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
              const float* bias, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
              const float* a_scale, const float* a_shift, int a_relu, const float* b_scale,
-             const float* b_shift, int b_relu, int split_k, float* workspace,
+             const float* b_shift, int b_relu, int split_k, float* workspace, float* stats_ws,
              spg_stream_t stream);
+/* Fused batch statistics: if stats_ws != NULL (needs split_k == 1) spg_gemm also writes, per
+ * 128-row tile and output column, (count, mean, M2) into stats_ws[spg_gemm_stats_tiles(M), N, 3];
+ * spg_colstats_merge folds n_partials such triples per column into mean[C], biased var[C].   */
+int64_t spg_gemm_stats_tiles(int64_t M);
+int spg_colstats_merge(const float* partials, int64_t n_partials, int C, float* mean, float* var,
+                       spg_stream_t stream);
 
 /* Per-column batch statistics of Y[M,C] (ld = ldy): mean[C], biased var[C];
  * workspace >= 3*C*spg_colstats_chunks(M) floats.  ref: nn.BatchNorm1d in training

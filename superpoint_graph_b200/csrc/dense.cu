@@ -33,6 +33,8 @@ struct GemmArgs {
     int b_relu;
     int64_t k_chunk;
     int a_vec, b_vec, c_vec, split;
+    float* stats;        // optional [row_tiles, N, 3] = (count, mean, M2) of C per 128-row tile
+    int64_t stats_tile0;  // first row-tile index of this launch (tall problems are slabbed)
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR>
@@ -245,6 +247,53 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs p) {
                 if (n + j < p.N) dst[j] = acc[i][j] + bv[j];
         }
     }
+    // fused batch statistics of this 128-row tile: two passes over the registers (sum -> mean,
+    // then sum of squared deviations), merged over tiles by colstats_merge (Chan, fp64).
+    if (p.stats) {
+        float* red = As;            // [16][64]
+        float* mean_s = As + 1024;  // [64]
+        __syncthreads();
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+            if (m0 + ty * TM + i < p.M)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cs[j] += acc[i][j] + bv[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[ty * 64 + tx * 4 + j] = cs[j];
+        __syncthreads();
+        const float nvalid = (float)min((int64_t)BM, p.M - m0);
+        if (t < 64) {
+            float tot = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) tot += red[r * 64 + t];
+            mean_s[t] = tot / nvalid;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cs[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+            if (m0 + ty * TM + i < p.M)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = acc[i][j] + bv[j] - mean_s[tx * 4 + j];
+                    cs[j] = fmaf(d, d, cs[j]);
+                }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[ty * 64 + tx * 4 + j] = cs[j];
+        __syncthreads();
+        if (t < 64 && n0 + t < p.N) {
+            float m2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) m2 += red[r * 64 + t];
+            float* o = p.stats + ((p.stats_tile0 + blockIdx.y) * p.N + n0 + t) * 3;
+            o[0] = nvalid;
+            o[1] = mean_s[t];
+            o[2] = m2;
+        }
+    }
 }
 
 __global__ void gemm_splitk_reduce_kernel(const float* __restrict__ ws, int split, int64_t M,
@@ -254,7 +303,16 @@ __global__ void gemm_splitk_reduce_kernel(const float* __restrict__ ws, int spli
     if (i >= M * N) return;
     const int64_t m = i / N, n = i % N;
     float s = 0.f;
-    for (int z = 0; z < split; ++z) s += ws[(int64_t)z * M * N + i];
+    const int64_t stride = M * N;
+    int z = 0;
+    for (; z + 8 <= split; z += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (int64_t)(z + u) * stride + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < split; ++z) s += __ldg(ws + (int64_t)z * stride + i);
     if (bias) s += bias[n];
     C[m * ldc + n] = s;
 }
@@ -303,12 +361,16 @@ colstats_partial_kernel(const float* __restrict__ Y, int64_t ldy, int64_t M, int
     }
 }
 
-__global__ void colstats_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
-                                      float* __restrict__ mean, float* __restrict__ var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per column: lanes merge strided subsets of the partials, then a shuffle tree
+// (Chan's parallel update, fp64) merges the 32 lane results.  Deterministic.
+__global__ void __launch_bounds__(128)
+colstats_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
+                      float* __restrict__ mean, float* __restrict__ var) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= C) return;
     double na = 0.0, ma = 0.0, qa = 0.0;
-    for (int64_t k = 0; k < chunks; ++k) {
+    for (int64_t k = lane; k < chunks; k += 32) {
         const float* o = ws + (k * C + c) * 3;
         const double nb = o[0], mb = o[1], qb = o[2];
         if (nb > 0.0) {
@@ -318,8 +380,25 @@ __global__ void colstats_final_kernel(const float* __restrict__ ws, int64_t chun
             na = nn;
         }
     }
-    mean[c] = (float)ma;
-    var[c] = na > 0.0 ? (float)(qa / na) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double nb = __shfl_xor_sync(0xffffffffu, na, o);
+        const double mb = __shfl_xor_sync(0xffffffffu, ma, o);
+        const double qb = __shfl_xor_sync(0xffffffffu, qa, o);
+        const double nn = na + nb;
+        if (nn > 0.0) {
+            // symmetric form so that both partners compute the same merged triple
+            const double d = mb - ma;
+            const double mnew = (na * ma + nb * mb) / nn;
+            qa = qa + qb + d * d * (na * nb / nn);
+            ma = mnew;
+            na = nn;
+        }
+    }
+    if (lane == 0) {
+        mean[c] = (float)ma;
+        var[c] = na > 0.0 ? (float)(qa / na) : 0.f;
+    }
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
@@ -475,9 +554,10 @@ extern "C" {
 int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
              const float* bias, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
              const float* a_scale, const float* a_shift, int a_relu, const float* b_scale,
-             const float* b_shift, int b_relu, int split_k, float* workspace,
+             const float* b_shift, int b_relu, int split_k, float* workspace, float* stats_ws,
              spg_stream_t stream) {
     if (M < 0 || N < 0 || K < 0) return SPG_E_BADARG;
+    if (stats_ws && split_k > 1) return SPG_E_UNSUPPORTED;
     if (M == 0 || N == 0) return SPG_OK;
     if (!A || !B || !C) return SPG_E_BADARG;
     if ((a_scale || a_shift || a_relu) && !a_kmajor) return SPG_E_UNSUPPORTED;
@@ -498,6 +578,8 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
     p.a_vec = a16(A) && (lda % 4 == 0);
     p.b_vec = a16(B) && (ldb % 4 == 0);
     p.c_vec = a16(C) && (ldc % 4 == 0);
+    p.stats = stats_ws;
+    p.stats_tile0 = 0;
     const int64_t gy = ceil_div64(M, BM), gx = ceil_div64(N, BN);
     if (gy > 65535 * 32ll) return SPG_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
@@ -508,6 +590,7 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
         const int64_t rows0 = y0 * BM;
         const int64_t gyi = min(max_gy, gy - y0);
         q.M = min(M - rows0, gyi * BM);
+        q.stats_tile0 = y0;
         if (a_kmajor) q.A = A + rows0 * lda; else q.A = A + rows0;
         if (split_k > 1) {
             if (gy > max_gy) return SPG_E_UNSUPPORTED;
@@ -536,12 +619,14 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
     return SPG_OK;
 }
 
-int64_t spg_colstats_chunks(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, kChunkRows); }
+// workspace bound for the column reductions (the vectorised kernels use 256-row chunks)
+int64_t spg_colstats_chunks(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, 256); }
+static inline int64_t scalar_chunks(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, kChunkRows); }
 
 int spg_colstats(const float* Y, int64_t ldy, int64_t M, int C, float* mean, float* var,
                  float* workspace, spg_stream_t stream) {
     if (M <= 0 || C <= 0 || !Y || !mean || !var || !workspace || ldy < C) return SPG_E_BADARG;
-    const int64_t chunks = spg_colstats_chunks(M);
+    const int64_t chunks = scalar_chunks(M);
     if (chunks > 65535) return SPG_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)chunks);
@@ -549,8 +634,18 @@ int spg_colstats(const float* Y, int64_t ldy, int64_t M, int C, float* mean, flo
                workspace);
     int rc = launch_status();
     if (rc) return rc;
-    SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, (unsigned)ceil_div64(C, 128), 128, 0,
+    SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, (unsigned)ceil_div64(C, 4), 128, 0,
                workspace, chunks, C, mean, var);
+    return launch_status();
+}
+
+int64_t spg_gemm_stats_tiles(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, BM); }
+
+int spg_colstats_merge(const float* partials, int64_t n_partials, int C, float* mean, float* var,
+                       spg_stream_t stream) {
+    if (n_partials <= 0 || C <= 0 || !partials || !mean || !var) return SPG_E_BADARG;
+    SPG_LAUNCH(K_COLSTATS_FINAL, (cudaStream_t)stream, colstats_final_kernel,
+               (unsigned)ceil_div64(C, 4), 128, 0, partials, n_partials, C, mean, var);
     return launch_status();
 }
 
@@ -578,6 +673,11 @@ int spg_affine_act(const float* Y, int64_t ldy, const float* scale, const float*
     if (M < 0 || C <= 0) return SPG_E_BADARG;
     if (M == 0) return SPG_OK;
     if (!Y || !out || ldy < C || ldo < C) return SPG_E_BADARG;
+    {
+        int rc = 0;
+        if (vec_affine_act(Y, ldy, scale, shift, relu, out, ldo, M, C, (cudaStream_t)stream, &rc))
+            return rc;
+    }
     dim3 grid((unsigned)ceil_div64(C, 32), rows_grid(M));
     SPG_LAUNCH(K_AFFINE_ACT, (cudaStream_t)stream, affine_act_kernel, grid, 256, 0, Y, ldy, scale,
                shift, relu, out, ldo, M, C);
@@ -587,7 +687,11 @@ int spg_affine_act(const float* Y, int64_t ldy, const float* scale, const float*
 int spg_colsum(const float* X, int64_t ldx, int64_t M, int C, float* out, float* workspace,
                spg_stream_t stream) {
     if (M <= 0 || C <= 0 || !X || !out || !workspace || ldx < C) return SPG_E_BADARG;
-    const int64_t chunks = spg_colstats_chunks(M);
+    {
+        int rc = 0;
+        if (vec_colsum(X, ldx, M, C, out, workspace, (cudaStream_t)stream, &rc)) return rc;
+    }
+    const int64_t chunks = scalar_chunks(M);
     if (chunks > 65535) return SPG_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)chunks);
@@ -606,7 +710,13 @@ int spg_act_bwd_reduce(const float* G, int64_t ldg, const float* Y, int64_t ldy,
     if (M <= 0 || C <= 0 || !G || !Y || !scale || !shift || !mean || !var || !s1 || !s2 ||
         !workspace)
         return SPG_E_BADARG;
-    const int64_t chunks = spg_colstats_chunks(M);
+    if (s2 == s1 + C) {
+        int rc = 0;
+        if (vec_act_bwd_reduce(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, s1, s2,
+                               workspace, M, C, (cudaStream_t)stream, &rc))
+            return rc;
+    }
+    const int64_t chunks = scalar_chunks(M);
     if (chunks > 65535) return SPG_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)chunks);
@@ -629,6 +739,12 @@ int spg_act_bwd_apply(const float* G, int64_t ldg, const float* Y, int64_t ldy,
     if (!G || !dY) return SPG_E_BADARG;
     if ((relu || has_bn) && !Y) return SPG_E_BADARG;
     if (has_bn && (!scale || !shift || !mean || !var || !s1 || !s2)) return SPG_E_BADARG;
+    {
+        int rc = 0;
+        if (vec_act_bwd_apply(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, has_bn, s1, s2,
+                              dY, lddy, M, C, (cudaStream_t)stream, &rc))
+            return rc;
+    }
     dim3 grid((unsigned)ceil_div64(C, 32), rows_grid(M));
     SPG_LAUNCH(K_ACT_BWD_APPLY, (cudaStream_t)stream, act_bwd_apply_kernel, grid, 256, 0, G, ldg, Y,
                ldy, scale, shift, mean, var, eps, relu, has_bn, s1, s2, dY, lddy, M, C);

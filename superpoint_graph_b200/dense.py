@@ -96,6 +96,18 @@ class Deferred(object):
         return ops.affine_act(self.raw, self.ld, M, self.C, self.scale, self.shift, self.relu)
 
 
+_ZEROS = {}
+
+
+def _zeros(n, device):
+    key = (n, device.index)
+    z = _ZEROS.get(key)
+    if z is None:
+        z = torch.zeros(n, dtype=torch.float32, device=device)
+        _ZEROS[key] = z
+    return z
+
+
 def _w2d(w):
     return w.view(w.shape[0], w.shape[1]) if w.dim() == 3 else w
 
@@ -107,15 +119,17 @@ def chain_forward(inp, M, specs, params, training, saved=None):
     for sp in specs:
         W = _w2d(params[sp.w])
         bias = params[sp.b] if sp.b is not None else None
-        y = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
-                     a_aff=cur.aff())
+        bn = sp.bn
+        batch_stats = bn is not None and (training or not bn.track_running_stats)
+        res = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
+                       a_aff=cur.aff(), stats=batch_stats)
         mean = var = scale = shift = None
-        if sp.bn is not None:
-            bn = sp.bn
+        y = res
+        if bn is not None:
             gamma = params[sp.gamma] if sp.gamma is not None else None
             beta = params[sp.beta] if sp.beta is not None else None
-            if training or not bn.track_running_stats:
-                mean, var = ops.colstats(y, sp.cout, M, sp.cout)
+            if batch_stats:
+                y, mean, var = res  # batch statistics come fused out of the GEMM epilogue
                 rm = rv = nbt = None
                 mom = 0.0
                 if training and bn.track_running_stats:
@@ -165,7 +179,13 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
         dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
         grads[sp.w] = dW.view(Wp.shape)
         if sp.b is not None:
-            grads[sp.b] = ops.colsum(dY, ldy, M, C)
+            if sp.bn is not None and nxt.scale is not None and mean is not None:
+                # a bias that feeds a batch-statistics BatchNorm has an analytically zero
+                # gradient (sum_m dY = -scale*s2/M * sum_m xhat = 0); the reference holds rounding
+                # noise there.  No reduction is launched.
+                grads[sp.b] = _zeros(C, dY.device)
+            else:
+                grads[sp.b] = ops.colsum(dY, ldy, M, C)
         if li > 0 or need_input_grad:
             G = ops.gemm(dY, ldy, True, _w2d(Wp), sp.cin, False, M, sp.cin, sp.cout)
             ldg = sp.cin

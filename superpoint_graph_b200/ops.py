@@ -207,7 +207,7 @@ def _auto_split(M, N, K):
 
 
 def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=None,
-         a_aff=None, b_aff=None, split_k=None):
+         a_aff=None, b_aff=None, split_k=None, stats=False):
     """C[M,N] = opA(A) opB(B) + bias.  a_aff/b_aff = (scale|None, shift|None, relu)."""
     _need_cuda(A, B)
     dev = A.device
@@ -220,16 +220,23 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
     b_s, b_t, b_r = b_aff if b_aff is not None else (None, None, False)
     GEMM_FLOPS[0] += 2 * M * N * K
     if split_k is None:
-        split_k = _auto_split(M, N, K)
+        split_k = 1 if stats else _auto_split(M, N, K)
     ws = workspace(split_k * M * N, dev) if split_k > 1 else None
+    tiles = (M + 127) // 128
+    sws = workspace(tiles * N * 3, dev) if stats else None
     _lib.call("spg_gemm", A, lda, int(a_kmajor), B, ldb, int(b_kmajor), bias, out, ldc, M, N, K,
-              a_s, a_t, int(bool(a_r)), b_s, b_t, int(bool(b_r)), split_k, ws,
+              a_s, a_t, int(bool(a_r)), b_s, b_t, int(bool(b_r)), split_k, ws, sws,
               _lib.current_stream())
+    if stats:
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        var = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.call("spg_colstats_merge", sws, tiles, N, mean, var, _lib.current_stream())
+        return out, mean, var
     return out
 
 
 def _chunks(M):
-    return max(1, (M + 1023) // 1024)
+    return max(1, (M + 255) // 256)
 
 
 def colstats(Y, ldy, M, C):
@@ -272,8 +279,8 @@ def colsum(X, ldx, M, C):
 
 def act_bwd_reduce(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, M, C):
     _need_cuda(G, Y)
-    s1 = torch.empty(C, dtype=torch.float32, device=G.device)
-    s2 = torch.empty(C, dtype=torch.float32, device=G.device)
+    s12 = torch.empty(2 * C, dtype=torch.float32, device=G.device)
+    s1, s2 = s12[:C], s12[C:]  # contiguous pair: one merge launch writes both
     ws = workspace(2 * C * _chunks(M), G.device)
     _lib.call("spg_act_bwd_reduce", G, ldg, Y, ldy, scale, shift, mean, var, float(eps),
               int(bool(relu)), s1, s2, ws, M, C, _lib.current_stream())
