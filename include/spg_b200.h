@@ -142,6 +142,21 @@ int64_t spg_gemm_stats_tiles(int64_t M);
 int spg_colstats_merge(const float* partials, int64_t n_partials, int C, float* mean, float* var,
                        spg_stream_t stream);
 
+/* tcgen05 tensor-core path of the same product for the large point-wise layers:
+ *   C[M,N] = f(A)[M,K] * B[N,K]^T + bias in fp32-equivalent precision (3xTF32 split, fp32 TMEM
+ *   accumulation), N in {64,128,256}, K % 32 == 0, lda/ldc % 4 == 0, 16-byte aligned pointers.
+ * B is given as a pre-split, pre-swizzled image built by spg_tc_pack_weights from W (ld = ldw):
+ *   transpose=0: B[n][k] = W[n][k] (forward, W = [N,K]); transpose=1: B[n][k] = W[k][n]
+ *   (data gradient, W = [K,N]).  image needs spg_tc_weight_image_floats(N,K) floats.
+ * stats_ws as in spg_gemm.  Returns SPG_E_UNSUPPORTED for other shapes (use spg_gemm).          */
+int64_t spg_tc_weight_image_floats(int N, int K);
+int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, float* image,
+                        spg_stream_t stream);
+int spg_tc_gemm_supported(int64_t M, int N, int K);
+int spg_tc_gemm(const float* A, int64_t lda, const float* weight_image, const float* bias, float* C,
+                int64_t ldc, int64_t M, int N, int K, const float* a_scale, const float* a_shift,
+                int a_relu, float* stats_ws, spg_stream_t stream);
+
 /* Per-column batch statistics of Y[M,C] (ld = ldy): mean[C], biased var[C];
  * workspace >= 3*C*spg_colstats_chunks(M) floats.  ref: nn.BatchNorm1d in training
  * mode (learning/pointnet.py:31,43,87,103; learning/graphnet.py:29).            */

@@ -41,6 +41,7 @@ enum KernelId {
     K_CE_LOSS_FINAL,
     K_CLAMP_ADAM,
     K_TC_GEMM,
+    K_TC_PACK,
     K_COUNT
 };
 

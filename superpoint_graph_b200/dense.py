@@ -121,8 +121,12 @@ def chain_forward(inp, M, specs, params, training, saved=None):
         bias = params[sp.b] if sp.b is not None else None
         bn = sp.bn
         batch_stats = bn is not None and (training or not bn.track_running_stats)
-        res = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
-                       a_aff=cur.aff(), stats=batch_stats)
+        if ops.tc_supported(M, sp.cout, sp.cin, cur.ld, sp.cout):
+            res = ops.tc_gemm(cur.raw, cur.ld, W, sp.cin, False, M, sp.cout, sp.cin, bias=bias,
+                              a_aff=cur.aff(), stats=batch_stats)
+        else:
+            res = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
+                           a_aff=cur.aff(), stats=batch_stats)
         mean = var = scale = shift = None
         y = res
         if bn is not None:
@@ -187,7 +191,10 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
             else:
                 grads[sp.b] = ops.colsum(dY, ldy, M, C)
         if li > 0 or need_input_grad:
-            G = ops.gemm(dY, ldy, True, _w2d(Wp), sp.cin, False, M, sp.cin, sp.cout)
+            if ops.tc_supported(M, sp.cin, sp.cout, ldy, sp.cin):
+                G = ops.tc_gemm(dY, ldy, _w2d(Wp), sp.cin, True, M, sp.cin, sp.cout)
+            else:
+                G = ops.gemm(dY, ldy, True, _w2d(Wp), sp.cin, False, M, sp.cin, sp.cout)
             ldg = sp.cin
             own_g = True
         else:

@@ -4,6 +4,8 @@ Every function takes CUDA tensors, validates shape/dtype/contiguity on the host 
 on torch's current stream.  CPU tensors are rejected: there is no CPU implementation in the
 product (the CPU restatement lives in oracle/ and is test infrastructure only).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -233,6 +235,40 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
         _lib.call("spg_colstats_merge", sws, tiles, N, mean, var, _lib.current_stream())
         return out, mean, var
     return out
+
+
+USE_TC = [os.environ.get("SPG_TC", "1") != "0"]  # tcgen05 path for the large point-wise layers
+
+
+def tc_supported(M, N, K, lda=0, ldc=0):
+    return (USE_TC[0] and M >= 512 and lda % 4 == 0 and ldc % 4 == 0
+            and bool(_lib.lib().spg_tc_gemm_supported(int(M), int(N), int(K))))
+
+
+def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False):
+    """C[M,N] = f(A)[M,K] B[N,K]^T + bias on the tcgen05 3xTF32 kernel.
+    transpose=False: B = W ([N,K], ld ldw); True: B = W^T with W [K,N]."""
+    _need_cuda(A, W)
+    dev = A.device
+    img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
+    _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, img, _lib.current_stream())
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
+    tiles = (M + 127) // 128
+    sws = workspace(tiles * N * 3, dev) if stats else None
+    GEMM_FLOPS[0] += 2 * M * N * K
+    TC_FLOPS[0] += 2 * M * N * K
+    _lib.call("spg_tc_gemm", A, lda, img, bias, out, N, M, N, K, a_s, a_t, int(bool(a_r)), sws,
+              _lib.current_stream())
+    if stats:
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        var = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.call("spg_colstats_merge", sws, tiles, N, mean, var, _lib.current_stream())
+        return out, mean, var
+    return out
+
+
+TC_FLOPS = [0]
 
 
 def _chunks(M):
