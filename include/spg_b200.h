@@ -157,6 +157,19 @@ int spg_tc_gemm(const float* A, int64_t lda, const float* weight_image, const fl
                 int64_t ldc, int64_t M, int N, int K, const float* a_scale, const float* a_shift,
                 int a_relu, float* stats_ws, spg_stream_t stream);
 
+/* Weight gradient of a point-wise layer on the tensor cores (3xTF32, fp32-equivalent):
+ *   dW[co,ci] = sum_m dY[m,co] * f(P)[m,ci],  f = affine(p_scale,p_shift)+ReLU of P's producer.
+ * co in {128,256}, ci in {64,128}; every CTA reduces a slab of points into a partial held in
+ * TMEM, workspace >= spg_tc_dw_ctas(M)*co*ci floats, partials are summed in a fixed order.
+ * C[M,N] = sum_z partials[z,M,N] (+ bias) is also exported on its own (spg_splitk_reduce).       */
+int spg_tc_dw_supported(int64_t M, int co, int ci);
+int spg_tc_dw_ctas(int64_t M);
+int spg_tc_dw(const float* dY, int64_t lddy, const float* P, int64_t ldp, const float* p_scale,
+              const float* p_shift, int p_relu, float* dW, float* workspace, int64_t M, int co, int ci,
+              spg_stream_t stream);
+int spg_splitk_reduce(const float* partials, int split, int64_t M, int64_t N, const float* bias,
+                      float* C, int64_t ldc, spg_stream_t stream);
+
 /* Per-column batch statistics of Y[M,C] (ld = ldy): mean[C], biased var[C];
  * workspace >= 3*C*spg_colstats_chunks(M) floats.  ref: nn.BatchNorm1d in training
  * mode (learning/pointnet.py:31,43,87,103; learning/graphnet.py:29).            */

@@ -42,6 +42,7 @@ enum KernelId {
     K_CLAMP_ADAM,
     K_TC_GEMM,
     K_TC_PACK,
+    K_TC_DW,
     K_COUNT
 };
 

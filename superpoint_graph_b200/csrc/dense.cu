@@ -620,6 +620,15 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
 }
 
 // workspace bound for the column reductions (the vectorised kernels use 256-row chunks)
+int spg_splitk_reduce(const float* partials, int split, int64_t M, int64_t N, const float* bias,
+                      float* C, int64_t ldc, spg_stream_t stream) {
+    if (!partials || !C || split < 1 || M <= 0 || N <= 0 || ldc < N) return SPG_E_BADARG;
+    const int64_t blocks = ceil_div64(M * N, 256);
+    SPG_LAUNCH(K_GEMM_SPLITK_REDUCE, (cudaStream_t)stream, gemm_splitk_reduce_kernel,
+               (unsigned)blocks, 256, 0, partials, split, M, N, bias, C, ldc);
+    return launch_status();
+}
+
 int64_t spg_colstats_chunks(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, 256); }
 static inline int64_t scalar_chunks(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, kChunkRows); }
 

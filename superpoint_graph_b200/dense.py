@@ -180,7 +180,10 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
             dY, ldy = G, ldg
         # weight gradient: dW[cout, cin] = dY^T [cout, M] * act(prev)[M, cin]
         Wp = params[sp.w]
-        dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
+        if ops.tc_dw_supported(M, sp.cout, sp.cin, ldy, cur.ld):
+            dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, sp.cin, p_aff=cur.aff())
+        else:
+            dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
         grads[sp.w] = dW.view(Wp.shape)
         if sp.b is not None:
             if sp.bn is not None and nxt.scale is not None and mean is not None:

@@ -271,6 +271,26 @@ def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=Fal
 TC_FLOPS = [0]
 
 
+def tc_dw_supported(M, co, ci, lddy, ldp):
+    return (USE_TC[0] and M >= 2048 and lddy % 4 == 0 and ldp % 4 == 0
+            and bool(_lib.lib().spg_tc_dw_supported(int(M), int(co), int(ci))))
+
+
+def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None):
+    """dW[co,ci] = dY^T [co,M] f(P)[M,ci] on the tcgen05 3xTF32 kernel."""
+    _need_cuda(dY, P)
+    dev = dY.device
+    ctas = int(_lib.lib().spg_tc_dw_ctas(int(M)))
+    ws = workspace(ctas * co * ci, dev)
+    out = torch.empty((co, ci), dtype=torch.float32, device=dev)
+    p_s, p_t, p_r = p_aff if p_aff is not None else (None, None, False)
+    GEMM_FLOPS[0] += 2 * M * co * ci
+    TC_FLOPS[0] += 2 * M * co * ci
+    _lib.call("spg_tc_dw", dY, lddy, P, ldp, p_s, p_t, int(bool(p_r)), out, ws, M, co, ci,
+              _lib.current_stream())
+    return out
+
+
 def _chunks(M):
     return max(1, (M + 255) // 256)
 

@@ -38,4 +38,17 @@ for (M, N, K) in [(128, 64, 32), (128, 64, 64), (1000, 64, 64), (4096, 128, 64),
     ok &= good
     print("M=%d N=%d K=%d  err %.2e  prologue %.2e  transposed %.2e  mean %.2e var %.2e  %s"
           % (M, N, K, e1, e2, e3, em, ev, "ok" if good else "FAIL"), flush=True)
+for (M, co, ci) in [(64, 128, 64), (4096, 128, 64), (5000, 128, 128), (100000, 256, 128), (3333, 256, 64)]:
+    dY = torch.randn(M, co, device=dev)
+    P = torch.randn(M, ci, device=dev)
+    sc, sh = torch.rand(ci, device=dev) + 0.5, torch.randn(ci, device=dev)
+    ref = dY.double().t() @ torch.relu(P.double() * sc.double() + sh.double())
+    out = ops.tc_dw(dY, co, P, ci, M, co, ci, p_aff=(sc, sh, True))
+    torch.cuda.synchronize()
+    e = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+    ref0 = dY.double().t() @ P.double()
+    e0 = ((ops.tc_dw(dY, co, P, ci, M, co, ci).double() - ref0).abs().max() / ref0.abs().max()).item()
+    good = max(e, e0) < 2e-5
+    ok &= good
+    print("dW M=%d co=%d ci=%d  err %.2e (plain %.2e) %s" % (M, co, ci, e, e0, "ok" if good else "FAIL"), flush=True)
 print("ALL OK" if ok else "SOME FAILED")
