@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
+    ap.add_argument("--trace-gemm", action="store_true", help="per-shape timing of the SIMT GEMM calls (stderr)")
     return ap.parse_args()
 
 
@@ -385,6 +386,18 @@ def run_b200(args):
         except Exception as ex:  # keep the bench line even if the microbench cannot run
             line["roofline_ecc_error"] = repr(ex)
 
+    if rank == 0 and world == 1 and args.trace_gemm:
+        ops.GEMM_TRACE = []
+        trainer.train_step(dbs[0])
+        torch.cuda.synchronize()
+        agg = {}
+        for desc, e0, e1 in ops.GEMM_TRACE:
+            a = agg.setdefault(desc, [0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+        ops.GEMM_TRACE = None
+        for desc, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+            print("[gemm_f32] %-40s x%d  %.3f ms" % (desc, n, ms), file=sys.stderr)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(batches[0], counts, margs, sd_ptn, sd_ecc)
     if rank == 0:

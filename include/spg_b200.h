@@ -153,6 +153,10 @@ int64_t spg_tc_weight_image_floats(int N, int K);
 int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, float* image,
                         spg_stream_t stream);
 int spg_tc_gemm_supported(int64_t M, int N, int K);
+/* kernel generation (1: one CTA per tile; 2, default: persistent warp-specialised, resident weights)
+ * and the number of statistics partials per column spg_tc_gemm writes for a given problem.     */
+int spg_tc_set_generation(int gen);
+int64_t spg_tc_gemm_stats_partials(int64_t M, int N, int K);
 int spg_tc_gemm(const float* A, int64_t lda, const float* weight_image, const float* bias, float* C,
                 int64_t ldc, int64_t M, int N, int K, const float* a_scale, const float* a_shift,
                 int a_relu, float* stats_ws, spg_stream_t stream);

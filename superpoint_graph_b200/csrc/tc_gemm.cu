@@ -252,6 +252,20 @@ extern "C" {
 
 int64_t spg_tc_weight_image_floats(int N, int K) { return (int64_t)2 * N * K; }
 
+static int g_tc_generation = 2;
+/* 1 = one CTA per row tile (tc_gemm.cu), 2 = persistent warp-specialised kernel (tc_gemm2.cu). */
+int spg_tc_set_generation(int gen) {
+    if (gen != 1 && gen != 2) return SPG_E_BADARG;
+    g_tc_generation = gen;
+    return SPG_OK;
+}
+
+/* number of (count, mean, M2) partials per column that spg_tc_gemm writes into stats_ws */
+int64_t spg_tc_gemm_stats_partials(int64_t M, int N, int K) {
+    const int64_t tiles = M <= 0 ? 1 : ceil_div64(M, TC_BM);
+    return (g_tc_generation == 2 && tc_gemm2_handles(N, K)) ? 4 * tiles : tiles;
+}
+
 int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, float* image,
                         spg_stream_t stream) {
     if (!W || !image || N <= 0 || K <= 0) return SPG_E_BADARG;
@@ -282,6 +296,12 @@ int spg_tc_gemm(const float* A, int64_t lda, const float* weight_image, const fl
     const int64_t tiles = ceil_div64(M, TC_BM);
     if (tiles > 2147483647ll) return SPG_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_tc_generation == 2) {
+        bool handled = false;
+        const int rc = tc_gemm2_try(A, lda, weight_image, bias, C, ldc, M, N, K, a_scale, a_shift,
+                                    a_relu, stats_ws, s, &handled);
+        if (handled) return rc;
+    }
     if (N == 64) return launch_tc<64>(a, tiles, s);
     if (N == 128) return launch_tc<128>(a, tiles, s);
     return launch_tc<256>(a, tiles, s);

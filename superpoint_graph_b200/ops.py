@@ -197,6 +197,7 @@ def gru_bwd(x, h, gy, w_ih, w_hh, b_ih, b_hh, w_ig, b_ig, flags, d_gi, d_gh, d_q
 
 
 # ---------------------------------------------------------------------------- dense
+GEMM_TRACE = None  # set to [] to record (description, start, end) events of every SIMT gemm call
 GEMM_FLOPS = [0]  # algorithmic FLOPs (2*M*N*K) issued through gemm(); read by bench.py
 
 
@@ -221,6 +222,9 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
     b_s, b_t, b_r = b_aff if b_aff is not None else (None, None, False)
     GEMM_FLOPS[0] += 2 * M * N * K
+    if GEMM_TRACE is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if split_k is None:
         split_k = 1 if stats else _auto_split(M, N, K)
     ws = workspace(split_k * M * N, dev) if split_k > 1 else None
@@ -229,6 +233,11 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
     _lib.call("spg_gemm", A, lda, int(a_kmajor), B, ldb, int(b_kmajor), bias, out, ldc, M, N, K,
               a_s, a_t, int(bool(a_r)), b_s, b_t, int(bool(b_r)), split_k, ws, sws,
               _lib.current_stream())
+    if GEMM_TRACE is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        GEMM_TRACE.append(("M=%d N=%d K=%d a%d b%d split=%d" % (M, N, K, int(a_kmajor), int(b_kmajor), split_k),
+                           ev0, ev1))
     if stats:
         mean = torch.empty(N, dtype=torch.float32, device=dev)
         var = torch.empty(N, dtype=torch.float32, device=dev)
@@ -254,7 +263,7 @@ def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=Fal
     _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, img, _lib.current_stream())
     out = torch.empty((M, N), dtype=torch.float32, device=dev)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
-    tiles = (M + 127) // 128
+    tiles = int(_lib.lib().spg_tc_gemm_stats_partials(int(M), int(N), int(K)))
     sws = workspace(tiles * N * 3, dev) if stats else None
     GEMM_FLOPS[0] += 2 * M * N * K
     TC_FLOPS[0] += 2 * M * N * K
