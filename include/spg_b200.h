@@ -139,19 +139,22 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
  * 128-row tile and output column, (count, mean, M2) into stats_ws[spg_gemm_stats_tiles(M), N, 3];
  * spg_colstats_merge folds n_partials such triples per column into mean[C], biased var[C].   */
 int64_t spg_gemm_stats_tiles(int64_t M);
-int spg_colstats_merge(const float* partials, int64_t n_partials, int C, float* mean, float* var,
+int spg_colstats_merge(float* partials, int64_t n_partials, int C, float* mean, float* var,
                        spg_stream_t stream);
+/* (the merge is two-level: `partials` needs room for ceil(n_partials/256) extra triples per column
+ *  after the n_partials*C*3 floats; the same holds for the workspaces of spg_colstats / stats_ws) */
 
 /* tcgen05 tensor-core path of the same product for the large point-wise layers:
  *   C[M,N] = f(A)[M,K] * B[N,K]^T + bias in fp32-equivalent precision (3xTF32 split, fp32 TMEM
  *   accumulation), N in {64,128,256}, K % 32 == 0, lda/ldc % 4 == 0, 16-byte aligned pointers.
  * B is given as a pre-split, pre-swizzled image built by spg_tc_pack_weights from W (ld = ldw):
  *   transpose=0: B[n][k] = W[n][k] (forward, W = [N,K]); transpose=1: B[n][k] = W[k][n]
- *   (data gradient, W = [K,N]).  image needs spg_tc_weight_image_floats(N,K) floats.
+ *   (data gradient, W = [K,N]).  image needs spg_tc_weight_image_floats(N,K) floats; entries with
+ *   k >= k_valid are zero (K padded to a multiple of 32, e.g. the 14 input features -> 32).
  * stats_ws as in spg_gemm.  Returns SPG_E_UNSUPPORTED for other shapes (use spg_gemm).          */
 int64_t spg_tc_weight_image_floats(int N, int K);
-int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, float* image,
-                        spg_stream_t stream);
+int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, int k_valid,
+                        float* image, spg_stream_t stream);
 int spg_tc_gemm_supported(int64_t M, int N, int K);
 /* kernel generation (1: one CTA per tile; 2, default: persistent warp-specialised, resident weights)
  * and the number of statistics partials per column spg_tc_gemm writes for a given problem.     */
@@ -163,7 +166,7 @@ int spg_tc_gemm(const float* A, int64_t lda, const float* weight_image, const fl
 
 /* Weight gradient of a point-wise layer on the tensor cores (3xTF32, fp32-equivalent):
  *   dW[co,ci] = sum_m dY[m,co] * f(P)[m,ci],  f = affine(p_scale,p_shift)+ReLU of P's producer.
- * co in {128,256}, ci in {64,128}; every CTA reduces a slab of points into a partial held in
+ * co in {64,128,256}, ci in {32,64,128}; every CTA reduces a slab of points into a partial held in
  * TMEM, workspace >= spg_tc_dw_ctas(M)*co*ci floats, partials are summed in a fixed order.
  * C[M,N] = sum_z partials[z,M,N] (+ bias) is also exported on its own (spg_splitk_reduce).       */
 int spg_tc_dw_supported(int64_t M, int co, int ci);

@@ -361,44 +361,96 @@ colstats_partial_kernel(const float* __restrict__ Y, int64_t ldy, int64_t M, int
     }
 }
 
-// One warp per column: lanes merge strided subsets of the partials, then a shuffle tree
-// (Chan's parallel update, fp64) merges the 32 lane results.  Deterministic.
-__global__ void __launch_bounds__(128)
+// Merge of (count, mean, M2) partials, deterministic and division-free in the inner loops:
+//   N = sum n_k, mean = sum n_k*mean_k / N, M2 = sum (M2_k + n_k*(mean_k - mean)^2)    (fp64 sums).
+// Block = 32 columns x 32 lanes, 256 partials per block (8 per thread, kept in registers between
+// the two passes); grid.y > 1 writes block-level partials (same triple format) for a second level.
+constexpr int kMergePerBlock = 256;
+
+__global__ void __launch_bounds__(1024)
 colstats_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
-                      float* __restrict__ mean, float* __restrict__ var) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (c >= C) return;
-    double na = 0.0, ma = 0.0, qa = 0.0;
-    for (int64_t k = lane; k < chunks; k += 32) {
-        const float* o = ws + (k * C + c) * 3;
-        const double nb = o[0], mb = o[1], qb = o[2];
-        if (nb > 0.0) {
-            const double nn = na + nb, d = mb - ma;
-            ma += d * (nb / nn);
-            qa += qb + d * d * (na * nb / nn);
-            na = nn;
-        }
-    }
+                      float* __restrict__ mean, float* __restrict__ var,
+                      float* __restrict__ out_partials) {
+    __shared__ double s_a[32][33], s_b[32][33];
+    __shared__ double s_mean[32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
+    const int64_t k0 = (int64_t)blockIdx.y * kMergePerBlock;
+    float pn[8], pm[8], pq[8];
+    double sn = 0.0, snm = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double nb = __shfl_xor_sync(0xffffffffu, na, o);
-        const double mb = __shfl_xor_sync(0xffffffffu, ma, o);
-        const double qb = __shfl_xor_sync(0xffffffffu, qa, o);
-        const double nn = na + nb;
-        if (nn > 0.0) {
-            // symmetric form so that both partners compute the same merged triple
-            const double d = mb - ma;
-            const double mnew = (na * ma + nb * mb) / nn;
-            qa = qa + qb + d * d * (na * nb / nn);
-            ma = mnew;
-            na = nn;
+    for (int u = 0; u < 8; ++u) {
+        const int64_t k = k0 + y + 32 * u;
+        pn[u] = 0.f;
+        pm[u] = 0.f;
+        pq[u] = 0.f;
+        if (c < C && k < chunks) {
+            const float* o = ws + (k * C + c) * 3;
+            pn[u] = o[0];
+            pm[u] = o[1];
+            pq[u] = o[2];
+        }
+        sn += (double)pn[u];
+        snm += (double)pn[u] * (double)pm[u];
+    }
+    s_a[y][x] = sn;
+    s_b[y][x] = snm;
+    __syncthreads();
+    if (y == 0) {
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < 32; ++j) {
+            a += s_a[j][x];
+            b += s_b[j][x];
+        }
+        s_a[0][x] = a;
+        s_mean[x] = a > 0.0 ? b / a : 0.0;
+    }
+    __syncthreads();
+    const double ntot = s_a[0][x], mu = s_mean[x];
+    double q = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const double d = (double)pm[u] - mu;
+        q += (double)pq[u] + (double)pn[u] * d * d;
+    }
+    __syncthreads();
+    s_b[y][x] = q;
+    __syncthreads();
+    if (y == 0 && c < C) {
+        double qq = 0.0;
+        for (int j = 0; j < 32; ++j) qq += s_b[j][x];
+        if (out_partials) {
+            float* o = out_partials + ((int64_t)blockIdx.y * C + c) * 3;
+            o[0] = (float)ntot;
+            o[1] = (float)mu;
+            o[2] = (float)qq;
+        } else {
+            mean[c] = (float)mu;
+            var[c] = ntot > 0.0 ? (float)(qq / ntot) : 0.f;
         }
     }
-    if (lane == 0) {
-        mean[c] = (float)ma;
-        var[c] = na > 0.0 ? (float)(qa / na) : 0.f;
+}
+
+// two-level driver; `partials` must have room for ceil(n/256) extra triples per column at its end
+static int colstats_merge_launch(float* partials, int64_t n, int C, float* mean, float* var,
+                                 cudaStream_t s) {
+    const unsigned gx = (unsigned)ceil_div64(C, 32);
+    const int64_t P = ceil_div64(n, kMergePerBlock);
+    if (P > 65535) return SPG_E_UNSUPPORTED;
+    if (P == 1) {
+        SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, dim3(gx, 1), 1024, 0, partials, n, C,
+                   mean, var, (float*)nullptr);
+        return launch_status();
     }
+    float* lvl2 = partials + n * C * 3;
+    SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, dim3(gx, (unsigned)P), 1024, 0, partials, n,
+               C, mean, var, lvl2);
+    int rc = launch_status();
+    if (rc) return rc;
+    if (P > kMergePerBlock) return SPG_E_UNSUPPORTED;
+    SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, dim3(gx, 1), 1024, 0, lvl2, P, C, mean, var,
+               (float*)nullptr);
+    return launch_status();
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
@@ -643,19 +695,15 @@ int spg_colstats(const float* Y, int64_t ldy, int64_t M, int C, float* mean, flo
                workspace);
     int rc = launch_status();
     if (rc) return rc;
-    SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, (unsigned)ceil_div64(C, 4), 128, 0,
-               workspace, chunks, C, mean, var);
-    return launch_status();
+    return colstats_merge_launch(workspace, chunks, C, mean, var, s);
 }
 
 int64_t spg_gemm_stats_tiles(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, BM); }
 
-int spg_colstats_merge(const float* partials, int64_t n_partials, int C, float* mean, float* var,
+int spg_colstats_merge(float* partials, int64_t n_partials, int C, float* mean, float* var,
                        spg_stream_t stream) {
     if (n_partials <= 0 || C <= 0 || !partials || !mean || !var) return SPG_E_BADARG;
-    SPG_LAUNCH(K_COLSTATS_FINAL, (cudaStream_t)stream, colstats_final_kernel,
-               (unsigned)ceil_div64(C, 4), 128, 0, partials, n_partials, C, mean, var);
-    return launch_status();
+    return colstats_merge_launch(partials, n_partials, C, mean, var, (cudaStream_t)stream);
 }
 
 int spg_bn_fold(const float* mean, const float* var, const float* gamma, const float* beta,

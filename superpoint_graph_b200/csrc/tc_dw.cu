@@ -46,14 +46,15 @@ __device__ __forceinline__ uint32_t mn_off(int pt, int c4) {
 
 template <int CO, int CI>
 __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
-    constexpr int MB_A = CO / 32, MB_B = CI / 32;
-    constexpr int A_BYTES = CO * DW_PTS * 4;  // one of hi|lo
+    constexpr int CO_PAD = CO < 128 ? 128 : CO;  // the accumulator tile has 128 rows (UMMA M)
+    constexpr int MB_A = CO_PAD / 32, MB_B = CI / 32;
+    constexpr int A_BYTES = CO_PAD * DW_PTS * 4;  // one of hi|lo
     constexpr int B_BYTES = CI * DW_PTS * 4;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr int MT = CO / 128;               // 128-row accumulator tiles
+    constexpr int MT = CO_PAD / 128;              // 128-row accumulator tiles
     constexpr int TMEM_COLS_RAW = MT * CI;
     constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-    static_assert(CO % 128 == 0 && CI % 32 == 0 && CI <= 256 && TMEM_COLS_RAW <= 512, "shape");
+    static_assert(CO % 64 == 0 && CI % 32 == 0 && CI <= 256 && TMEM_COLS_RAW <= 512, "shape");
     constexpr int A_F4 = CO * DW_PTS / 4 / DW_THREADS;  // float4 per thread per chunk
     constexpr int B_F4 = CI * DW_PTS / 4 / DW_THREADS;
 
@@ -83,6 +84,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    if (CO < CO_PAD) {
+        // channels CO..127 of the A tiles are never written by the loads: zero them once
+        for (int i = t; i < 2 * STAGE_BYTES / 16; i += DW_THREADS)
+            reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+    }
 
     const int64_t m_beg = (int64_t)blockIdx.x * p.pts_per_cta;
     const int64_t m_end = min(p.M, m_beg + p.pts_per_cta);
@@ -207,6 +214,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const int row = mt * 128 + q * 32 + lane;
+            if (row >= CO) continue;  // padded accumulator rows
             for (int cb = half; cb < NBLK; cb += 2) {
                 float4* dst = reinterpret_cast<float4*>(out + (int64_t)row * CI + cb * 32);
                 if (nchunks > 0) {
@@ -241,7 +249,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
 
 template <int CO, int CI>
 static int launch_dw(const DwArgs& a, int ctas, cudaStream_t s) {
-    constexpr int STAGE_BYTES = 2 * CO * DW_PTS * 4 + 2 * CI * DW_PTS * 4;
+    constexpr int CO_PAD = CO < 128 ? 128 : CO;
+    constexpr int STAGE_BYTES = 2 * CO_PAD * DW_PTS * 4 + 2 * CI * DW_PTS * 4;
     const int smem = 2 * STAGE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc_dw_kernel<CO, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
@@ -256,8 +265,8 @@ using namespace spg;
 extern "C" {
 
 int spg_tc_dw_supported(int64_t M, int co, int ci) {
-    const bool co_ok = (co == 128 || co == 256);
-    const bool ci_ok = (ci == 64 || ci == 128);
+    const bool co_ok = (co == 64 || co == 128 || co == 256);
+    const bool ci_ok = (ci == 32 || ci == 64 || ci == 128);
     return (M >= DW_PTS && co_ok && ci_ok) ? 1 : 0;
 }
 
@@ -282,10 +291,12 @@ int spg_tc_dw(const float* dY, int64_t lddy, const float* P, int64_t ldp, const 
     a.pts_per_cta = ceil_div64(ceil_div64(M, ctas), DW_PTS) * DW_PTS;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (co == 128 && ci == 64) rc = launch_dw<128, 64>(a, ctas, s);
-    else if (co == 128 && ci == 128) rc = launch_dw<128, 128>(a, ctas, s);
-    else if (co == 256 && ci == 64) rc = launch_dw<256, 64>(a, ctas, s);
-    else rc = launch_dw<256, 128>(a, ctas, s);
+#define SPG_DW_CASE(CO_, CI_) \
+    if (co == CO_ && ci == CI_) rc = launch_dw<CO_, CI_>(a, ctas, s); else
+    SPG_DW_CASE(64, 32) SPG_DW_CASE(64, 64) SPG_DW_CASE(64, 128) SPG_DW_CASE(128, 32)
+    SPG_DW_CASE(128, 64) SPG_DW_CASE(128, 128) SPG_DW_CASE(256, 32) SPG_DW_CASE(256, 64)
+    SPG_DW_CASE(256, 128) rc = SPG_E_UNSUPPORTED;
+#undef SPG_DW_CASE
     if (rc) return rc;
     return spg_splitk_reduce(workspace, ctas, co, ci, nullptr, dW, ci, stream);
 }

@@ -31,11 +31,12 @@ constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;  // 16 KB per (hi|lo) A tile
 // out exactly as the shared-memory tile (SWIZZLE_128B).  transpose=0: B[n][k] = W[n*ldw + k];
 // transpose=1: B[n][k] = W[k*ldw + n] (the data-gradient GEMM consumes W^T).
 __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int64_t ldw, int transpose,
-                                       int N, int K, float* __restrict__ img) {
+                                       int N, int K, int k_valid, float* __restrict__ img) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     const int n = (int)(i / K), k = (int)(i % K);
-    const float v = transpose ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
+    float v = 0.f;  // k >= k_valid: zero padding of the reduction dimension
+    if (k < k_valid) v = transpose ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
     const uint32_t hi = to_tf32(v);
     const uint32_t lo = to_tf32(v - __uint_as_float(hi));
     const int kc = k / TC_KC, kk = k % TC_KC;
@@ -266,13 +267,13 @@ int64_t spg_tc_gemm_stats_partials(int64_t M, int N, int K) {
     return (g_tc_generation == 2 && tc_gemm2_handles(N, K)) ? 4 * tiles : tiles;
 }
 
-int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, float* image,
-                        spg_stream_t stream) {
-    if (!W || !image || N <= 0 || K <= 0) return SPG_E_BADARG;
+int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, int k_valid,
+                        float* image, spg_stream_t stream) {
+    if (!W || !image || N <= 0 || K <= 0 || k_valid <= 0 || k_valid > K) return SPG_E_BADARG;
     if (K % TC_KC != 0 || N % 8 != 0) return SPG_E_UNSUPPORTED;
     const int64_t total = (int64_t)N * K;
     SPG_LAUNCH(K_TC_PACK, (cudaStream_t)stream, tc_pack_weights_kernel,
-               (unsigned)ceil_div64(total, 256), 256, 0, W, ldw, transpose, N, K, image);
+               (unsigned)ceil_div64(total, 256), 256, 0, W, ldw, transpose, N, K, k_valid, image);
     return launch_status();
 }
 

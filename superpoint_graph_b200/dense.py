@@ -108,6 +108,12 @@ def _zeros(n, device):
     return z
 
 
+def _padded_k(cin, ld):
+    """cin rounded up to a multiple of 32 if the rows are wide enough to be read that far."""
+    kp = (cin + 31) // 32 * 32
+    return kp if kp <= ld else cin
+
+
 def _w2d(w):
     return w.view(w.shape[0], w.shape[1]) if w.dim() == 3 else w
 
@@ -121,9 +127,12 @@ def chain_forward(inp, M, specs, params, training, saved=None):
         bias = params[sp.b] if sp.b is not None else None
         bn = sp.bn
         batch_stats = bn is not None and (training or not bn.track_running_stats)
-        if ops.tc_supported(M, sp.cout, sp.cin, cur.ld, sp.cout):
-            res = ops.tc_gemm(cur.raw, cur.ld, W, sp.cin, False, M, sp.cout, sp.cin, bias=bias,
-                              a_aff=cur.aff(), stats=batch_stats)
+        kpad = _padded_k(sp.cin, cur.ld)
+        if ops.tc_supported(M, sp.cout, kpad, cur.ld, sp.cout) and (kpad == sp.cin or not cur.pending):
+            # reduction dimension zero-padded to a multiple of 32 (the rows are zero-padded to
+            # cur.ld and the weight image gets zeros there)
+            res = ops.tc_gemm(cur.raw, cur.ld, W, sp.cin, False, M, sp.cout, kpad, bias=bias,
+                              a_aff=cur.aff(), stats=batch_stats, k_valid=sp.cin)
         else:
             res = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
                            a_aff=cur.aff(), stats=batch_stats)
@@ -180,8 +189,11 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
             dY, ldy = G, ldg
         # weight gradient: dW[cout, cin] = dY^T [cout, M] * act(prev)[M, cin]
         Wp = params[sp.w]
-        if ops.tc_dw_supported(M, sp.cout, sp.cin, ldy, cur.ld):
-            dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, sp.cin, p_aff=cur.aff())
+        kpad = _padded_k(sp.cin, cur.ld)
+        if ops.tc_dw_supported(M, sp.cout, kpad, ldy, cur.ld) and (kpad == sp.cin or not cur.pending):
+            dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, kpad, p_aff=cur.aff())
+            if kpad != sp.cin:
+                dW = dW[:, :sp.cin].contiguous()
         else:
             dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
         grads[sp.w] = dW.view(Wp.shape)

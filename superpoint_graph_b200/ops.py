@@ -203,9 +203,9 @@ GEMM_FLOPS = [0]  # algorithmic FLOPs (2*M*N*K) issued through gemm(); read by b
 
 def _auto_split(M, N, K):
     tiles = ((M + 127) // 128) * ((N + 63) // 64)
-    if tiles >= 148 or K < 1024:
+    if tiles >= 148 or K < 256:
         return 1
-    split = min((2 * 148 + tiles - 1) // tiles, max(1, K // 256))
+    split = min((2 * 148 + tiles - 1) // tiles, max(1, K // 64))
     return max(1, split)
 
 
@@ -229,7 +229,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
         split_k = 1 if stats else _auto_split(M, N, K)
     ws = workspace(split_k * M * N, dev) if split_k > 1 else None
     tiles = (M + 127) // 128
-    sws = workspace(tiles * N * 3, dev) if stats else None
+    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev) if stats else None
     _lib.call("spg_gemm", A, lda, int(a_kmajor), B, ldb, int(b_kmajor), bias, out, ldc, M, N, K,
               a_s, a_t, int(bool(a_r)), b_s, b_t, int(bool(b_r)), split_k, ws, sws,
               _lib.current_stream())
@@ -254,17 +254,18 @@ def tc_supported(M, N, K, lda=0, ldc=0):
             and bool(_lib.lib().spg_tc_gemm_supported(int(M), int(N), int(K))))
 
 
-def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False):
+def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False, k_valid=None):
     """C[M,N] = f(A)[M,K] B[N,K]^T + bias on the tcgen05 3xTF32 kernel.
     transpose=False: B = W ([N,K], ld ldw); True: B = W^T with W [K,N]."""
     _need_cuda(A, W)
     dev = A.device
     img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
-    _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, img, _lib.current_stream())
+    _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K,
+              int(K if k_valid is None else k_valid), img, _lib.current_stream())
     out = torch.empty((M, N), dtype=torch.float32, device=dev)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
     tiles = int(_lib.lib().spg_tc_gemm_stats_partials(int(M), int(N), int(K)))
-    sws = workspace(tiles * N * 3, dev) if stats else None
+    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev) if stats else None
     GEMM_FLOPS[0] += 2 * M * N * K
     TC_FLOPS[0] += 2 * M * N * K
     _lib.call("spg_tc_gemm", A, lda, img, bias, out, N, M, N, K, a_s, a_t, int(bool(a_r)), sws,
@@ -286,7 +287,8 @@ def tc_dw_supported(M, co, ci, lddy, ldp):
 
 
 def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None):
-    """dW[co,ci] = dY^T [co,M] f(P)[M,ci] on the tcgen05 3xTF32 kernel."""
+    """dW[co,ci] = dY^T [co,M] f(P)[M,ci] on the tcgen05 3xTF32 kernel (ci may be the padded
+    leading dimension of P; the caller slices the valid columns)."""
     _need_cuda(dY, P)
     dev = dY.device
     ctas = int(_lib.lib().spg_tc_dw_ctas(int(M)))
@@ -308,7 +310,7 @@ def colstats(Y, ldy, M, C):
     _need_cuda(Y)
     mean = torch.empty(C, dtype=torch.float32, device=Y.device)
     var = torch.empty(C, dtype=torch.float32, device=Y.device)
-    ws = workspace(3 * C * _chunks(M), Y.device)
+    ws = workspace(3 * C * (_chunks(M) + _chunks(M) // 256 + 2), Y.device)
     _lib.call("spg_colstats", Y, ldy, M, C, mean, var, ws, _lib.current_stream())
     return mean, var
 

@@ -33,6 +33,12 @@ def _round4(n):
     return (n + 3) // 4 * 4
 
 
+def _row_ld(nfeat):
+    """Leading dimension of the point-major input rows: zero-padded to 32 floats (one 128-byte
+    swizzle row) so that the first layer runs on the tensor-core path as well."""
+    return 32 if nfeat <= 32 else _round4(nfeat)
+
+
 class STNkD(nn.Module):
     """Spatial transformer producing a KxK matrix per cloud (ref: learning/pointnet.py:16-61)."""
 
@@ -114,7 +120,7 @@ class _StnFunction(torch.autograd.Function):
         clouds = clouds.contiguous()
         B, F, L = clouds.shape
         groups, _ = _stn_params(stn, training)
-        ld = _round4(F)
+        ld = _row_ld(F)
         rows = ops.cloud_rows(clouds, None, ld)
         saved = {} if training else None
         T = _stn_forward(rows, ld, B, L, groups, params, training, saved)
@@ -217,7 +223,7 @@ class _PointNetFunction(torch.autograd.Function):
             raise TypeError("PointNet kernels are float32")
         B, F, L = clouds.shape
         M = B * L
-        ld = _round4(F)
+        ld = _row_ld(F)
         saved = {} if training else None
         T = None
         if nfeat_stn > 0:

@@ -25,16 +25,16 @@ for (N, K) in [(64, 64), (128, 64), (128, 128), (256, 128), (64, 128), (128, 256
     A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
     sc, sh = torch.rand(K, device=dev), torch.randn(K, device=dev)
     img = torch.empty(2 * N * K, device=dev)
-    _lib.call("spg_tc_pack_weights", W, K, 0, N, K, img, _lib.current_stream())
+    _lib.call("spg_tc_pack_weights", W, K, 0, N, K, K, img, _lib.current_stream())
     out = torch.empty(M, N, device=dev)
     tiles = 4 * ((M + 127) // 128)
-    sws = torch.empty(tiles * N * 3, device=dev)
+    sws = torch.empty((tiles + 64) * N * 3, device=dev)
     def run(stats=True, pro=True):
         _lib.call("spg_tc_gemm", A, K, img, b, out, N, M, N, K, sc if pro else None, sh if pro else None, int(pro),
                   sws if stats else None, _lib.current_stream())
     t = timeit(run)
     t2 = timeit(lambda: run(False, False))
-    tp = timeit(lambda: _lib.call("spg_tc_pack_weights", W, K, 0, N, K, img, _lib.current_stream()))
+    tp = timeit(lambda: _lib.call("spg_tc_pack_weights", W, K, 0, N, K, K, img, _lib.current_stream()))
     ts = timeit(lambda: ops.gemm(A, K, True, W, K, True, M, N, K, bias=b, a_aff=(sc, sh, True), stats=False))
     fl = 2.0 * M * N * K
     by = 4.0 * M * (N + K)
@@ -58,7 +58,7 @@ print("act_bwd_reduce [M,128]: %.1f us (%.2f TB/s)" % (t, 8.0 * M * C / t / 1e6)
 s1, s2 = ops.act_bwd_reduce(G, C, Y, C, scale, shift, mean, var, 1e-5, True, M, C)
 t = timeit(lambda: ops.act_bwd_apply(G, C, Y, C, scale, shift, mean, var, 1e-5, True, True, s1, s2, M, C))
 print("act_bwd_apply  [M,128]: %.1f us (%.2f TB/s)" % (t, 12.0 * M * C / t / 1e6))
-sws = torch.randn(((M + 127) // 128) * C * 3, device=dev).abs()
+sws = torch.randn((4 * ((M + 127) // 128) + 64) * C * 3, device=dev).abs()
 mo, vo = torch.empty(C, device=dev), torch.empty(C, device=dev)
-t = timeit(lambda: _lib.call("spg_colstats_merge", sws, (M + 127) // 128, C, mo, vo, _lib.current_stream()))
+t = timeit(lambda: _lib.call("spg_colstats_merge", sws, 4 * ((M + 127) // 128), C, mo, vo, _lib.current_stream()))
 print("colstats_merge %d partials x %d cols: %.1f us" % ((M + 127) // 128, C, t))
