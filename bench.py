@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--trace-gemm", action="store_true", help="per-shape timing of the SIMT GEMM calls (stderr)")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA-graph replay)")
     return ap.parse_args()
 
 
@@ -302,21 +303,64 @@ def run_b200(args):
     total_ms, all_units = float(tt), float(uu)
     value = all_units / (total_ms * 1e-3)
 
+    eager_ms, eager_value = total_ms / args.steps, value
+    # ---- same K steps replayed from CUDA graphs (one per distinct batch shape): identical kernels,
+    # one graph launch per step instead of ~200 kernel launches
+    graph_keys, graph_err = None, None
+    if not args.no_graph:
+        try:
+            per_step0 = ops.total_launches()
+            graph_keys = [trainer.capture(dbs[i], key=i, warmup=1) for i in range(4)]
+            launches_per_step = (ops.total_launches() - per_step0) // 8  # (1 warm-up + 1 capture) x 4
+            for i in range(args.warmup):
+                trainer.replay(graph_keys[i % 4])
+            barrier()
+            sampler = ClockSampler(local)
+            sampler.start()
+            evs, done_units = [], 0
+            t_wall = time.perf_counter()
+            for i in range(args.steps):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                trainer.replay(graph_keys[i % 4])
+                e.record()
+                evs.append((s, e))
+                done_units += units[i % 4]
+            barrier()
+            wall = time.perf_counter() - t_wall
+            clocks = sampler.stop()
+            launches = launches_per_step * args.steps
+            total_ms = sum(s.elapsed_time(e) for s, e in evs)
+            tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            uu = torch.tensor([float(done_units)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+            total_ms, all_units = float(tt), float(uu)
+            value = all_units / (total_ms * 1e-3)
+        except Exception as ex:  # keep the eager numbers
+            graph_keys, graph_err = None, repr(ex)
+
     # ---- end-to-end through the public API with host buffers (H2D + step + D2H of loss/logits)
     h2d = hbs[0].h2d_bytes()
     out_host = torch.empty((args.nodes, margs.classes), dtype=torch.float32).pin_memory()
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    def e2e_step(i):
+        if graph_keys is not None:  # refresh the graph's static input buffers, then replay
+            hbs[i % 4].copy_into(dbs[i % 4])
+            return trainer.replay(graph_keys[i % 4])
+        return trainer.train_step(hbs[i % 4].to_device(dev))
+
     for i in range(0 if args.no_e2e else max(3, args.warmup // 2)):
-        db = hbs[i % 4].to_device(dev)
-        trainer.train_step(db)
+        e2e_step(i)
     barrier()
     e2e_ms, e2e_units = 1e-9, 0
     for i in range(0 if args.no_e2e else args.steps):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        db = hbs[i % 4].to_device(dev)
-        loss, logits = trainer.train_step(db)
+        loss, logits = e2e_step(i)
         out_host[:logits.shape[0]].copy_(logits, non_blocking=True)
         loss_host.copy_(loss, non_blocking=True)
         e.record()
@@ -344,11 +388,15 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(t2) / args.steps},
         "gpu_launches": int(launches),
+        "cuda_graph": graph_keys is not None,
+        "eager": {"ms_per_step": eager_ms, "value": eager_value},
         "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
         "clocks": clocks,
         "peaks": pk["source"],
     }
 
+    if graph_err:
+        line["cuda_graph_error"] = graph_err
     if rank == 0 and not args.no_roofline:
         # per-kernel shares of the step (events around every launch; separate, untimed pass)
         ops.prof_reset()

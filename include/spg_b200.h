@@ -252,6 +252,14 @@ int spg_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_a
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                    float grad_clip, float grad_scale, int64_t step, spg_stream_t stream);
 
+/* Same update, step count kept in device memory (*step_counter is read as step-1 and incremented
+ * by the call): nothing step-dependent is baked into launch parameters, so the whole training
+ * step can be captured in a CUDA graph and replayed.                                          */
+int spg_clamp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float grad_clip, float grad_scale, int64_t* step_counter,
+                       spg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

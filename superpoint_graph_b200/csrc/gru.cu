@@ -10,7 +10,6 @@
 
 namespace spg {
 
-constexpr int kRW = 4;        // rows processed together by one warp
 constexpr int kGruWarps = 8;  // warps per block
 
 // shared-memory layout (floats):
@@ -19,7 +18,7 @@ constexpr int kGruWarps = 8;  // warps per block
 //   Whh_t [H][3H+1]
 //   per warp scratch: hrow[RW][H], xrow[RW][H], srow[RW][H], gi[RW][3H], gh[RW][3H]
 __host__ __device__ inline int gru_weight_floats(int H) { return H * (H + 1) + 2 * H * (3 * H + 1); }
-__host__ __device__ inline int gru_scratch_floats(int H) { return kRW * (3 * H + 6 * H); }
+__host__ __device__ inline int gru_scratch_floats(int H, int rw) { return rw * (3 * H + 6 * H); }
 
 __device__ __forceinline__ void gru_load_weights(float* sm, const float* __restrict__ w_ih,
                                                  const float* __restrict__ w_hh,
@@ -45,6 +44,7 @@ __device__ __forceinline__ void gru_load_weights(float* sm, const float* __restr
 // Recomputes everything up to the normalised gate inputs for RW rows.
 // On return (per row i): hrow = h, xrow = gated input x', srow = sigmoid(q) (or 1),
 // gi/gh = raw (pre-norm) gate inputs, stats = {mean_i, rstd_i, mean_h, rstd_h}.
+template <int kRW>
 __device__ __forceinline__ void gru_rows_forward(const float* sm, float* scratch, int H, int flags,
                                                  const float* __restrict__ x,
                                                  const float* __restrict__ h,
@@ -142,6 +142,7 @@ __device__ __forceinline__ void gru_rows_forward(const float* sm, float* scratch
     }
 }
 
+template <int kRW>
 __global__ void __launch_bounds__(kGruWarps * 32)
 gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
                const float* __restrict__ w_ih, const float* __restrict__ w_hh,
@@ -152,7 +153,7 @@ gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     gru_load_weights(sm, w_ih, w_hh, w_ig, H, flags & SPG_GRU_INGATE);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H);
+    float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H, kRW);
     const float* hrow = scratch;
     const float* gi = scratch + 3 * kRW * H;
     const float* gh = gi + kRW * 3 * H;
@@ -162,7 +163,7 @@ gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     for (int64_t row0 = ((int64_t)blockIdx.x * kGruWarps + warp) * kRW; row0 < n_rows;
          row0 += warps_total * kRW) {
         float st[kRW][4];
-        gru_rows_forward(sm, scratch, H, flags, x, h, b_ig, row0, n_rows, lane, st);
+        gru_rows_forward<kRW>(sm, scratch, H, flags, x, h, b_ig, row0, n_rows, lane, st);
         for (int c = lane; c < H; c += 32) {
             const float bir = has_bias ? b_ih[c] : 0.f, biz = has_bias ? b_ih[H + c] : 0.f,
                         bin = has_bias ? b_ih[2 * H + c] : 0.f;
@@ -189,7 +190,7 @@ gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     }
 }
 
-template <int NU>
+template <int NU, int kRW>
 __global__ void __launch_bounds__(kGruWarps * 32)
 gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
                const float* __restrict__ gy, const float* __restrict__ w_ih,
@@ -206,7 +207,7 @@ gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     const float* Wih_t = Wig_t + H * (H + 1);
     const float* Whh_t = Wih_t + H * (3 * H + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H);
+    float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H, kRW);
     float* hrow = scratch;
     float* xrow = hrow + kRW * H;   // x' (gated input)
     float* srow = xrow + kRW * H;   // sigmoid(q); reused below for d_q
@@ -220,7 +221,7 @@ gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     for (int64_t row0 = ((int64_t)blockIdx.x * kGruWarps + warp) * kRW; row0 < n_rows;
          row0 += warps_total * kRW) {
         float st[kRW][4];
-        gru_rows_forward(sm, scratch, H, flags, x, h, b_ig, row0, n_rows, lane, st);
+        gru_rows_forward<kRW>(sm, scratch, H, flags, x, h, b_ig, row0, n_rows, lane, st);
         // ---- gate gradients (w.r.t. the normalised gate inputs), in place over gi/gh
         float dh_direct[kRW][NU];  // column c = lane + 32*u
 #pragma unroll
@@ -385,8 +386,14 @@ gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     }
 }
 
-static inline size_t gru_smem_bytes(int H) {
-    return sizeof(float) * ((size_t)gru_weight_floats(H) + (size_t)kGruWarps * gru_scratch_floats(H));
+static inline size_t gru_smem_bytes(int H, int rw) {
+    return sizeof(float) * ((size_t)gru_weight_floats(H) + (size_t)kGruWarps * gru_scratch_floats(H, rw));
+}
+
+// rows per warp: 4 amortises the shared-memory weight reads when there are enough rows to fill
+// the GPU; small graphs (the S3DIS training batches) use 1 so that every row gets its own warp.
+static inline int gru_rows_per_warp(int64_t n_rows) {
+    return n_rows >= (int64_t)kNumSMs * kGruWarps * 4 * 2 ? 4 : 1;
 }
 
 }  // namespace spg
@@ -404,16 +411,23 @@ int spg_gru_fwd(const float* x, const float* h, const float* weight_ih, const fl
     if (!x || !h || !weight_ih || !weight_hh || !hy) return SPG_E_BADARG;
     if ((flags & SPG_GRU_BIAS) && (!bias_ih || !bias_hh)) return SPG_E_BADARG;
     if ((flags & SPG_GRU_INGATE) && (!ig_weight || !ig_bias)) return SPG_E_BADARG;
-    const size_t smem = gru_smem_bytes(hidden);
+    const int rw = gru_rows_per_warp(n_rows);
+    const size_t smem = gru_smem_bytes(hidden, rw);
     if (hidden > 128 || smem > 227 * 1024) return SPG_E_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int64_t blocks = ceil_div64(n_rows, (int64_t)kGruWarps * kRW);
+    int64_t blocks = ceil_div64(n_rows, (int64_t)kGruWarps * rw);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-    SPG_LAUNCH(K_GRU_FWD, (cudaStream_t)stream, gru_fwd_kernel, (unsigned)blocks, kGruWarps * 32,
-               smem, x, h, weight_ih, weight_hh, bias_ih, bias_hh, ig_weight, ig_bias, hy, n_rows,
-               hidden, flags);
+#define SPG_GRU_FWD_CASE(RW)                                                                      \
+    {                                                                                             \
+        cudaError_t e = cudaFuncSetAttribute(gru_fwd_kernel<RW>,                                  \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                             (int)smem);                                          \
+        if (e != cudaSuccess) return (int)e;                                                      \
+        SPG_LAUNCH(K_GRU_FWD, (cudaStream_t)stream, gru_fwd_kernel<RW>, (unsigned)blocks,         \
+                   kGruWarps * 32, smem, x, h, weight_ih, weight_hh, bias_ih, bias_hh, ig_weight, \
+                   ig_bias, hy, n_rows, hidden, flags);                                           \
+    }
+    if (rw == 4) { SPG_GRU_FWD_CASE(4) } else { SPG_GRU_FWD_CASE(1) }
+#undef SPG_GRU_FWD_CASE
     return launch_status();
 }
 
@@ -429,17 +443,19 @@ int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const floa
         return SPG_E_BADARG;
     if ((flags & SPG_GRU_BIAS) && (!bias_ih || !bias_hh)) return SPG_E_BADARG;
     if ((flags & SPG_GRU_INGATE) && (!ig_weight || !ig_bias)) return SPG_E_BADARG;
-    const size_t smem = gru_smem_bytes(hidden);
+    const int rw = gru_rows_per_warp(n_rows);
+    const size_t smem = gru_smem_bytes(hidden, rw);
     if (hidden > 128 || smem > 227 * 1024) return SPG_E_UNSUPPORTED;
-    int64_t blocks = ceil_div64(n_rows, (int64_t)kGruWarps * kRW);
+    int64_t blocks = ceil_div64(n_rows, (int64_t)kGruWarps * rw);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-#define SPG_GRU_BWD_CASE(NU)                                                                      \
+#define SPG_GRU_BWD_CASE(NU) { SPG_GRU_BWD_CASE2(NU, 4) else SPG_GRU_BWD_CASE2(NU, 1) }
+#define SPG_GRU_BWD_CASE2(NU, RW) if (rw == RW)                                                                      \
     {                                                                                             \
-        cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<NU>,                                  \
+        cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<NU, RW>,                                  \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                              (int)smem);                                          \
         if (e != cudaSuccess) return (int)e;                                                      \
-        SPG_LAUNCH(K_GRU_BWD, (cudaStream_t)stream, gru_bwd_kernel<NU>, (unsigned)blocks,         \
+        SPG_LAUNCH(K_GRU_BWD, (cudaStream_t)stream, (gru_bwd_kernel<NU, RW>), (unsigned)blocks,         \
                    kGruWarps * 32, smem, x, h, grad_hy, weight_ih, weight_hh, bias_ih, bias_hh,   \
                    ig_weight, ig_bias, d_x, d_h, d_gi, d_gh, d_q, xprime, dpre, n_rows, hidden,   \
                    flags);                                                                        \
@@ -448,6 +464,7 @@ int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const floa
     else if (hidden <= 64) SPG_GRU_BWD_CASE(2)
     else SPG_GRU_BWD_CASE(4)
 #undef SPG_GRU_BWD_CASE
+#undef SPG_GRU_BWD_CASE2
     return launch_status();
 }
 

@@ -71,6 +71,32 @@ clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
     }
 }
 
+// Same update with the step count read from device memory (CUDA-graph friendly: nothing about the
+// step is baked into the launch parameters).  step = *counter + 1.
+__global__ void __launch_bounds__(256)
+clamp_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                      float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                      float wd, float clip, float gscale, const long long* __restrict__ counter) {
+    const double step = (double)(counter[0] + 1);
+    const float bc1 = (float)(1.0 - pow((double)b1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+__global__ void counter_increment_kernel(long long* counter) { counter[0] += 1; }
+
 }  // namespace spg
 
 using namespace spg;
@@ -109,6 +135,26 @@ int spg_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_a
     SPG_LAUNCH(K_CLAMP_ADAM, (cudaStream_t)stream, clamp_adam_kernel, (unsigned)blocks, 256, 0,
                param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_clip,
                grad_scale, (float)bc1, (float)sqrt(bc2));
+    return launch_status();
+}
+
+
+int spg_clamp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float grad_clip, float grad_scale, int64_t* step_counter,
+                       spg_stream_t stream) {
+    if (n < 0 || !step_counter) return SPG_E_BADARG;
+    if (n == 0) return SPG_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return SPG_E_BADARG;
+    int64_t blocks = ceil_div64(n, 256);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    cudaStream_t s = (cudaStream_t)stream;
+    SPG_LAUNCH(K_CLAMP_ADAM, s, clamp_adam_dev_kernel, (unsigned)blocks, 256, 0, param, grad, exp_avg,
+               exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_clip, grad_scale,
+               (const long long*)step_counter);
+    int rc = launch_status();
+    if (rc) return rc;
+    SPG_LAUNCH(K_CLAMP_ADAM, s, counter_increment_kernel, 1, 1, 0, (long long*)step_counter);
     return launch_status();
 }
 

@@ -441,6 +441,15 @@ def clamp_adam_(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.9
               float(grad_scale), int(step), _lib.current_stream())
 
 
+def clamp_adam_dev_(param, grad, exp_avg, exp_avg_sq, step_counter, lr, beta1=0.9, beta2=0.999,
+                    eps=1e-8, weight_decay=0.0, grad_clip=0.0, grad_scale=1.0):
+    """clamp + Adam with the step count in device memory (int64 scalar tensor, incremented here)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, step_counter)
+    _lib.call("spg_clamp_adam_dev", param, grad, exp_avg, exp_avg_sq, param.numel(), float(lr),
+              float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_clip),
+              float(grad_scale), step_counter, _lib.current_stream())
+
+
 # ------------------------------------------------------------------------ profiling
 def prof_enable(on):
     _lib.lib().spg_prof_enable(int(on))

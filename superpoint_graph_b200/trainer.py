@@ -101,6 +101,16 @@ class HostBatch(object):
         return d
 
 
+    def copy_into(self, d):
+        """Asynchronous H2D refresh of an existing DeviceBatch of the same shapes (static buffers of a
+        captured CUDA graph)."""
+        for f in self.FIELDS:
+            getattr(d, f).copy_(getattr(self, f), non_blocking=True)
+        dev = d.gi.graph()._dev[(d.clouds.device.type, d.clouds.device.index)]
+        for k, v in self.graph_pinned.items():
+            dev[k].copy_(v, non_blocking=True)
+
+
 class DeviceBatch(object):
     pass
 
@@ -115,6 +125,8 @@ class Trainer(object):
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
+        self.step_dev = torch.zeros((), dtype=torch.int64, device=self.flat.device)
+        self._graphs = {}
         self.class_weights = class_weights
         self.pg, self.world_size = process_group, world_size
         if world_size > 1:  # one-time setup collective: guarantee identical replicas
@@ -140,10 +152,31 @@ class Trainer(object):
         if self.world_size > 1:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         self.step_count += 1
-        ops.clamp_adam_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
-                        lr=self.args.lr, weight_decay=self.args.wd, grad_clip=self.args.grad_clip,
-                        grad_scale=1.0 / self.world_size)
+        ops.clamp_adam_dev_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
+                            lr=self.args.lr, weight_decay=self.args.wd, grad_clip=self.args.grad_clip,
+                            grad_scale=1.0 / self.world_size)
         return loss, logits.detach()
+
+    # ---- CUDA-graph replay for batches whose shapes repeat (fixed-size evaluation resampling,
+    # synthetic sweeps).  The step is static given the shapes: one capture, then one graph launch per
+    # step instead of ~200 kernel launches.  Batches of new shapes simply run eagerly.
+    def capture(self, db, key=None, warmup=2):
+        """Captures train_step on the static tensors of `db`; returns the key for replay()."""
+        key = key if key is not None else id(db)
+        for _ in range(warmup):
+            self.train_step(db)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss, logits = self.train_step(db)
+        self._graphs[key] = (g, db, loss, logits)
+        return key
+
+    def replay(self, key):
+        g, db, loss, logits = self._graphs[key]
+        g.replay()
+        self.step_count += 1
+        return loss, logits
 
     @torch.no_grad()
     def eval_step(self, db):
