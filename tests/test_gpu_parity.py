@@ -469,3 +469,38 @@ def test_cpu_tensors_are_rejected(dev):
     from superpoint_graph_b200 import ops
     with pytest.raises(RuntimeError):
         ops.gemm(torch.randn(4, 4), 4, True, torch.randn(4, 4), 4, True, 4, 4, 4)
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    """Trainer.capture()/replay(): three replayed steps == three eager steps (same kernels, same
+    order; the Adam step count lives in device memory so nothing is baked into the graph)."""
+    from superpoint_graph_b200.synthetic import make_batch
+    from superpoint_graph_b200.trainer import HostBatch, Trainer, create_model, make_args
+    args = make_args(model_config="gru_3_1_1_1_0,f_13")
+    batch = make_batch(n_nodes=200, seed=11)
+    results = []
+    for mode in ("eager", "graph"):
+        torch.manual_seed(5)
+        model = create_model(args)
+        model.to(dev)
+        tr = Trainer(model, args)
+        db = HostBatch(batch).to_device(dev)
+        losses = []
+        if mode == "eager":
+            for _ in range(3):
+                loss, logits = tr.train_step(db)
+                losses.append(float(loss[0]))
+        else:
+            # 1 eager warm-up step; the capture pass only records (nothing executes), then 2 replays
+            key = tr.capture(db, warmup=1)
+            losses = [None]
+            for _ in range(2):
+                loss, logits = tr.replay(key)
+                losses.append(float(loss[0]))
+        torch.cuda.synchronize()
+        results.append((losses, tr.flat.clone(), logits.clone()))
+    (l_e, p_e, o_e), (l_g, p_g, o_g) = results
+    assert int(torch.isfinite(p_g).all())
+    close(torch.tensor(l_g[1:]), torch.tensor(l_e[1:]), 1e-5)
+    close(o_g, o_e, 1e-4)
+    close(p_g, p_e, 1e-4, 2.1e-2 * 4)  # noise-driven (pre-BN bias) parameters random-walk by +-lr
