@@ -401,7 +401,8 @@ def run_b200(args):
         # per-kernel shares of the step (events around every launch; separate, untimed pass)
         ops.prof_reset()
         ops.prof_enable(1)
-        flops0 = ops.GEMM_FLOPS[0]
+        flops0 = {"gemm_f32": ops.GEMM_FLOPS[0] - ops.TC_FLOPS[0] - ops.DW_FLOPS[0],
+                  "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0]}
         nprof = 3
         for i in range(nprof):
             trainer.train_step(dbs[i % 4]) if world == 1 else None
@@ -412,14 +413,24 @@ def run_b200(args):
             tot = sum(v[1] for v in ks.values())
             top = sorted(ks.items(), key=lambda kv: -kv[1][1])
             line["kernel_shares"] = {k: {"launches_per_step": v[0] / nprof, "ms_per_step": v[1] / nprof,
-                                         "share": v[1] / tot} for k, v in top[:10]}
-            gname, (gl, gms) = top[0]
-            if gname == "gemm_f32":
-                flops = (ops.GEMM_FLOPS[0] - flops0)
-                ach = flops / (gms * 1e-3) / 1e12
-                line["roofline"] = {"kernel": gname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
-                                    "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
-                                    "note": "exact-fp32 FMA GEMM (SIMT) measured against the bf16 tensor peak"}
+                                         "share": v[1] / tot} for k, v in top[:12]}
+            flops1 = {"gemm_f32": ops.GEMM_FLOPS[0] - ops.TC_FLOPS[0] - ops.DW_FLOPS[0],
+                      "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0]}
+            notes = {"gemm_f32": "exact-fp32 FMA GEMM (small/odd shapes), measured against the bf16 tensor peak",
+                     "tc_gemm_3xtf32": "tcgen05 kind::tf32, 3 MMAs per product (error-compensated split, fp32-"
+                                       "equivalent): algorithmic FLOPs counted once; ceiling = bf16 peak / 6",
+                     "tc_dw_3xtf32": "tcgen05 kind::tf32 MN-major operands, 3 MMAs per product; ceiling = bf16 peak / 6"}
+            dense = {}
+            for name in ("tc_gemm_3xtf32", "tc_dw_3xtf32", "gemm_f32"):
+                if name in ks and ks[name][1] > 0:
+                    ach = (flops1[name] - flops0[name]) / (ks[name][1] * 1e-3) / 1e12
+                    dense[name] = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
+                                   "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                                   "share_of_step": ks[name][1] / tot, "note": notes[name]}
+            gname = top[0][0]
+            if gname in dense:
+                line["roofline"] = dense[gname]
+            line["roofline_dense_kernels"] = dense
         try:
             er = ecc_roofline(dev, args.ecc_nodes, pk)
             line["roofline_ecc"] = er

@@ -278,7 +278,8 @@ def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=Fal
     return out
 
 
-TC_FLOPS = [0]
+TC_FLOPS = [0]  # algorithmic FLOPs through tc_gemm (forward + data gradients)
+DW_FLOPS = [0]  # algorithmic FLOPs through tc_dw (weight gradients)
 
 
 def tc_dw_supported(M, co, ci, lddy, ldp):
@@ -296,7 +297,7 @@ def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None):
     out = torch.empty((co, ci), dtype=torch.float32, device=dev)
     p_s, p_t, p_r = p_aff if p_aff is not None else (None, None, False)
     GEMM_FLOPS[0] += 2 * M * co * ci
-    TC_FLOPS[0] += 2 * M * co * ci
+    DW_FLOPS[0] += 2 * M * co * ci
     _lib.call("spg_tc_dw", dY, lddy, P, ldp, p_s, p_t, int(bool(p_r)), out, ws, M, co, ci,
               _lib.current_stream())
     return out
