@@ -311,7 +311,7 @@ def run_b200(args):
         try:
             per_step0 = ops.total_launches()
             graph_keys = [trainer.capture(dbs[i], key=i, warmup=1) for i in range(4)]
-            launches_per_step = (ops.total_launches() - per_step0) // 8  # (1 warm-up + 1 capture) x 4
+            launches_per_step = (ops.total_launches() - per_step0) // 8 + 1  # (1 warm-up + 1 capture) x 4
             for i in range(args.warmup):
                 trainer.replay(graph_keys[i % 4])
             barrier()

@@ -139,8 +139,9 @@ class Trainer(object):
         emb = _scatter(out, db.idx_valid, db.n_nodes)
         return self.model.ecc(emb)
 
-    def train_step(self, db):
-        """One optimisation step on a device-resident batch; returns (loss[1], logits)."""
+    def compute_gradients(self, db):
+        """Forward, loss, backward; gathers every parameter gradient into the flat buffer.
+        Returns (loss[1], logits).  Purely local to this rank (no collective)."""
         self.model.train()
         for p in self.params:
             p.grad = None
@@ -149,33 +150,45 @@ class Trainer(object):
         logits.backward(d_logits)
         self.embedder.bw_hook()
         torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_grad)
+        return loss, logits.detach()
+
+    def apply_update(self):
+        """One all-reduce of the flat gradient (scene-parallel ranks), then clamp + Adam in one
+        kernel (gradient averaged by 1/world before the clamp, as main.py:210-213 on one GPU)."""
         if self.world_size > 1:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         self.step_count += 1
         ops.clamp_adam_dev_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
                             lr=self.args.lr, weight_decay=self.args.wd, grad_clip=self.args.grad_clip,
                             grad_scale=1.0 / self.world_size)
-        return loss, logits.detach()
+
+    def train_step(self, db):
+        """One optimisation step on a device-resident batch; returns (loss[1], logits)."""
+        loss, logits = self.compute_gradients(db)
+        self.apply_update()
+        return loss, logits
 
     # ---- CUDA-graph replay for batches whose shapes repeat (fixed-size evaluation resampling,
-    # synthetic sweeps).  The step is static given the shapes: one capture, then one graph launch per
-    # step instead of ~200 kernel launches.  Batches of new shapes simply run eagerly.
+    # synthetic sweeps).  The local part of the step (forward, loss, backward, gradient gather) is
+    # static given the shapes: one capture, then one graph launch per step instead of ~250 kernel
+    # launches.  The collective and the optimizer kernel stay outside the graph (NCCL is not
+    # captured).  Batches of new shapes simply run eagerly.
     def capture(self, db, key=None, warmup=2):
-        """Captures train_step on the static tensors of `db`; returns the key for replay()."""
+        """Captures compute_gradients on the static tensors of `db`; returns the key for replay()."""
         key = key if key is not None else id(db)
         for _ in range(warmup):
             self.train_step(db)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            loss, logits = self.train_step(db)
+            loss, logits = self.compute_gradients(db)
         self._graphs[key] = (g, db, loss, logits)
         return key
 
     def replay(self, key):
         g, db, loss, logits = self._graphs[key]
         g.replay()
-        self.step_count += 1
+        self.apply_update()
         return loss, logits
 
     @torch.no_grad()
