@@ -29,49 +29,53 @@ __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
     return c;
 }
 
-// One 8-lane group per target node; 4 edges in flight per group.
+// One warp per target node: lane = (slot = lane>>3, sub = lane&7); the 4 slots walk the node's
+// edges interleaved (4 independent gather chains per node, 2 edges in flight per slot), the 8 sub
+// lanes cover the 32 channels with float4.  Slot partials are combined with two shuffles.
 __global__ void __launch_bounds__(256)
 ecc_vv_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ w,
                   const int* __restrict__ rowptr, const int* __restrict__ idxn,
                   float4* __restrict__ out, int n_out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t node = t / kG;
-    const int sub = (int)(t % kG);
+    const int lane = threadIdx.x & 31;
+    const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_out) return;
+    const int slot = lane >> 3, sub = lane & 7;
     const int beg = rowptr[node], end = rowptr[node + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int e = beg;
-    for (; e + 4 <= end; e += 4) {
-        const int s0 = __ldg(idxn + e), s1 = __ldg(idxn + e + 1), s2 = __ldg(idxn + e + 2),
-                  s3 = __ldg(idxn + e + 3);
+    int e = beg + slot;
+    for (; e + 4 < end; e += 8) {
+        const int s0 = __ldg(idxn + e), s1 = __ldg(idxn + e + 4);
         const float4 w0 = ld_stream4(w + (int64_t)e * kG + sub);
-        const float4 w1 = ld_stream4(w + (int64_t)(e + 1) * kG + sub);
-        const float4 w2 = ld_stream4(w + (int64_t)(e + 2) * kG + sub);
-        const float4 w3 = ld_stream4(w + (int64_t)(e + 3) * kG + sub);
+        const float4 w1 = ld_stream4(w + (int64_t)(e + 4) * kG + sub);
         const float4 x0 = __ldg(x + (int64_t)s0 * kG + sub);
         const float4 x1 = __ldg(x + (int64_t)s1 * kG + sub);
-        const float4 x2 = __ldg(x + (int64_t)s2 * kG + sub);
-        const float4 x3 = __ldg(x + (int64_t)s3 * kG + sub);
         acc = fma4(x0, w0, acc);
         acc = fma4(x1, w1, acc);
-        acc = fma4(x2, w2, acc);
-        acc = fma4(x3, w3, acc);
     }
-    for (; e < end; ++e) {
+    if (e < end) {
         const int s0 = __ldg(idxn + e);
         const float4 w0 = ld_stream4(w + (int64_t)e * kG + sub);
         const float4 x0 = __ldg(x + (int64_t)s0 * kG + sub);
         acc = fma4(x0, w0, acc);
     }
-    const int deg = end - beg;
-    if (deg > 0) {
-        const float d = (float)deg;
-        acc.x /= d;
-        acc.y /= d;
-        acc.z /= d;
-        acc.w /= d;
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    out[node * kG + sub] = acc;
+    if (slot == 0) {
+        const int deg = end - beg;
+        if (deg > 0) {
+            const float d = (float)deg;
+            acc.x /= d;
+            acc.y /= d;
+            acc.z /= d;
+            acc.w /= d;
+        }
+        out[node * kG + sub] = acc;
+    }
 }
 
 // Matrix filters W_e [32,32] (4 KB per edge): one warp per target node.  A warp
@@ -211,23 +215,24 @@ ecc_mat_bwd_w_kernel(const float* __restrict__ xs, const float4* __restrict__ gs
 }
 
 // grad_x[j,:] = add0 + add1 + sum_{e out of j} w[e,:] * g[t_e,:]/deg_t  (vector filters)
+// warp per source node, 4 edge slots x 8 channel lanes (as the forward kernel).
 __global__ void __launch_bounds__(256)
 ecc_vv_bwd_x_kernel(const float4* __restrict__ w, const float4* __restrict__ g,
                     const int* __restrict__ tgt_rowptr, const int* __restrict__ src_rowptr,
                     const int* __restrict__ src_perm, const int* __restrict__ edge_tgt,
                     const float4* __restrict__ add0, const float4* __restrict__ add1,
                     float4* __restrict__ grad_x, int n_in) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t node = t / kG;
-    const int sub = (int)(t % kG);
+    const int lane = threadIdx.x & 31;
+    const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_in) return;
+    const int slot = lane >> 3, sub = lane & 7;
     const int beg = src_rowptr[node], end = src_rowptr[node + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = beg; p < end; ++p) {
+    for (int p = beg + slot; p < end; p += 4) {
         const int e = __ldg(src_perm + p);
         const int tg = __ldg(edge_tgt + e);
-        const float inv = 1.f / (float)(__ldg(tgt_rowptr + tg + 1) - __ldg(tgt_rowptr + tg));
         const float4 wv = __ldg(w + (int64_t)e * kG + sub);
+        const float inv = 1.f / (float)(__ldg(tgt_rowptr + tg + 1) - __ldg(tgt_rowptr + tg));
         float4 gv = __ldg(g + (int64_t)tg * kG + sub);
         gv.x *= inv;
         gv.y *= inv;
@@ -235,21 +240,30 @@ ecc_vv_bwd_x_kernel(const float4* __restrict__ w, const float4* __restrict__ g,
         gv.w *= inv;
         acc = fma4(wv, gv, acc);
     }
-    if (add0) {
-        const float4 a = add0[node * kG + sub];
-        acc.x += a.x;
-        acc.y += a.y;
-        acc.z += a.z;
-        acc.w += a.w;
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    if (add1) {
-        const float4 a = add1[node * kG + sub];
-        acc.x += a.x;
-        acc.y += a.y;
-        acc.z += a.z;
-        acc.w += a.w;
+    if (slot == 0) {
+        if (add0) {
+            const float4 a = add0[node * kG + sub];
+            acc.x += a.x;
+            acc.y += a.y;
+            acc.z += a.z;
+            acc.w += a.w;
+        }
+        if (add1) {
+            const float4 a = add1[node * kG + sub];
+            acc.x += a.x;
+            acc.y += a.y;
+            acc.z += a.z;
+            acc.w += a.w;
+        }
+        grad_x[node * kG + sub] = acc;
     }
-    grad_x[node * kG + sub] = acc;
 }
 
 // grad_x[j,k] = add0 + add1 + sum_{e out of j} sum_o W_e[k,o] * g[t_e,o]/deg_t
@@ -436,7 +450,7 @@ int spg_ecc_fwd(const void* x, const void* w, const int32_t* tgt_rowptr, const i
                        (const float*)x, (const float4*)w, tgt_rowptr, idxn, (float4*)out,
                        (int)n_out);
         } else {
-            const int64_t blocks = ceil_div64(n_out * kG, 256);
+            const int64_t blocks = ceil_div64(n_out * 32, 256);
             SPG_LAUNCH(K_ECC_VV_FWD, s, ecc_vv_fwd_kernel, (unsigned)blocks, 256, 0,
                        (const float4*)x, (const float4*)w, tgt_rowptr, idxn, (float4*)out,
                        (int)n_out);
@@ -522,7 +536,7 @@ int spg_ecc_bwd_x(const void* w, const void* g, const int32_t* tgt_rowptr,
                        edge_tgt, (const float*)add0, (const float*)add1, (float*)grad_x,
                        (int)n_in);
         } else {
-            const int64_t blocks = ceil_div64(n_in * kG, 256);
+            const int64_t blocks = ceil_div64(n_in * 32, 256);
             SPG_LAUNCH(K_ECC_VV_BWD_X, s, ecc_vv_bwd_x_kernel, (unsigned)blocks, 256, 0,
                        (const float4*)w, (const float4*)g, tgt_rowptr, src_rowptr, src_perm,
                        edge_tgt, (const float4*)add0, (const float4*)add1, (float4*)grad_x,
