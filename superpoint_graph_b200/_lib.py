@@ -82,18 +82,21 @@ def error_string(code):
     return lib().spg_error_string(int(code)).decode()
 
 
-def _conv(arg):
-    """torch.Tensor -> device pointer; None -> NULL; python numbers pass through."""
-    if arg is None:
-        return None
-    if hasattr(arg, "data_ptr"):
-        return ctypes.c_void_p(arg.data_ptr())
-    return arg
+_fns = {}
+_Tensor = None
 
 
 def call(name, *args):
-    fn = getattr(lib(), name)
-    rc = fn(*[_conv(a) for a in args])
+    """Calls a C-ABI entry point: tensors become device pointers (plain ints), None becomes NULL.
+    Kept lean on purpose: an eager training step makes ~250 of these calls."""
+    global _Tensor
+    fn = _fns.get(name)
+    if fn is None:
+        import torch
+
+        _Tensor = torch.Tensor
+        fn = _fns[name] = getattr(lib(), name)
+    rc = fn(*[a.data_ptr() if isinstance(a, _Tensor) else a for a in args])
     if rc != 0:
         raise RuntimeError("%s failed: [%d] %s" % (name, rc, error_string(rc)))
 
@@ -101,4 +104,4 @@ def call(name, *args):
 def current_stream():
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream

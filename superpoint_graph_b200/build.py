@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-] + (["-DSPG_DW_DEBUG"] if os.environ.get("SPG_DW_DEBUG") else [])
+]
 
 
 def _nvcc():

@@ -13,8 +13,6 @@
 //
 // Reference semantics: the weight gradient of nn.Conv1d(k=1) (learning/pointnet.py:29,85) as
 // autograd computes it; the reference materialises ReLU(BN(P)) and runs cuDNN/cuBLAS on it.
-#include <stdio.h>
-
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -95,11 +93,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
     const int64_t m_end = min(p.M, m_beg + p.pts_per_cta);
     const int nchunks = m_beg < m_end ? (int)((m_end - m_beg + DW_PTS - 1) / DW_PTS) : 0;
     constexpr uint32_t idesc = umma_idesc_tf32_major(128, CI, 1, 1);
-#ifdef SPG_DW_DEBUG
-    if (t == 0 && blockIdx.x == 0)
-        printf("dw: M=%lld pts_per_cta=%lld m_beg=%lld m_end=%lld nchunks=%d tmem=%08x idesc=%08x\n",
-               (long long)p.M, (long long)p.pts_per_cta, (long long)m_beg, (long long)m_end, nchunks, tmem_base, idesc);
-#endif
     const bool pro = p.p_scale || p.p_shift || p.p_relu;
 
     float4 ra[A_F4], rb[B_F4];
@@ -220,12 +213,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
                 if (nchunks > 0) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * CI + cb * 32), r);
-#ifdef SPG_DW_DEBUG
-                    if (blockIdx.x == 0 && t == 0 && cb == 0)
-                        printf("dw: acc[0][0..3] = %f %f %f %f ; smem a_hi[0]=%f b_hi[0]=%f\n", __uint_as_float(r[0]),
-                               __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]),
-                               *reinterpret_cast<float*>(smem), *reinterpret_cast<float*>(smem + 2 * A_BYTES));
-#endif
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
