@@ -228,6 +228,14 @@ int spg_segmax_fwd(const float* Y, int64_t ldy, const float* scale, const float*
 /* G[b*L+l,c] = (l==argmax[b,c]) ? g_pooled[b,c] : 0 (G fully written).              */
 int spg_segmax_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax, float* G,
                    int64_t ldG, int64_t B, int L, int C, spg_stream_t stream);
+/* Max-pool backward fused with the BatchNorm(+ReLU) backward of the layer Y that fed the pool:
+ * s12 = [s1|s2] (= d_beta | d_gamma, 2*C floats) and dY[B*L,C] are produced straight from the pooled
+ * gradient and the argmax; the dense gradient of the pooled activation is never materialised.
+ * workspace >= 2*C*ceil(B/256) floats.  C % 4 == 0.                                            */
+int spg_segmax_bn_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax, const float* Y,
+                      int64_t ldy, const float* scale, const float* shift, const float* mean,
+                      const float* var, float eps, int relu, float* s12, float* dY, int64_t lddy,
+                      float* workspace, int64_t B, int L, int C, spg_stream_t stream);
 /* dT[b,i,j] = sum_l xy[b,i,l] * dXrows[b*L+l, j], i,j in {0,1}; clouds is the raw
  * [B,F,L] input, dXrows has leading dimension ld.                                    */
 int spg_stn_apply_bwd(const float* clouds, const float* dXrows, int64_t ld, float* dT, int64_t B,

@@ -136,6 +136,104 @@ stn_apply_bwd_kernel(const float* __restrict__ clouds, const float* __restrict__
                                   red[3][threadIdx.x];
 }
 
+// ---- max-pool backward fused with the BatchNorm+ReLU backward of the layer that fed the pool.
+// The gradient w.r.t. the pooled activation is non-zero at one point per (cloud, channel) only, so
+// the batch reductions s1 = sum G*mask, s2 = sum G*mask*xhat need just the argmax rows ...
+// grid (ceil(C/32), ceil(B/256)); block 32 x 8; partial layout [chunk][2][C] (as act_bwd_reduce).
+__global__ void __launch_bounds__(256)
+segmax_bn_bwd_reduce_kernel(const float* __restrict__ gp, int64_t ldg, const int* __restrict__ argmax,
+                            const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
+                            const float* __restrict__ shift, const float* __restrict__ mean,
+                            const float* __restrict__ var, float eps, int relu,
+                            float* __restrict__ ws, int64_t B, int L, int C) {
+    __shared__ float s1[8][32], s2[8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
+    const int64_t b0 = (int64_t)blockIdx.y * 256, b1 = min(B, b0 + 256);
+    float a1 = 0.f, a2 = 0.f;
+    if (c < C) {
+        const float sc = scale[c], sh = shift[c], mu = mean[c];
+        const float rstd = 1.f / sqrtf(var[c] + eps);
+        for (int64_t b = b0 + y; b < b1; b += 8) {
+            const int l = argmax[b * C + c];
+            const float yv = __ldg(Y + (b * L + l) * ldy + c);
+            float g = __ldg(gp + b * ldg + c);
+            if (relu && !(fmaf(yv, sc, sh) > 0.f)) g = 0.f;
+            a1 += g;
+            a2 = fmaf(g, (yv - mu) * rstd, a2);
+        }
+    }
+    s1[y][x] = a1;
+    s2[y][x] = a2;
+    __syncthreads();
+    if (y == 0 && c < C) {
+        float t1 = 0.f, t2 = 0.f;
+        for (int j = 0; j < 8; ++j) {
+            t1 += s1[j][x];
+            t2 += s2[j][x];
+        }
+        ws[((int64_t)blockIdx.y * 2) * C + c] = t1;
+        ws[((int64_t)blockIdx.y * 2 + 1) * C + c] = t2;
+    }
+}
+
+// ... and dY = scale*(G*mask - s1/M - xhat*s2/M) is written directly from (g_pooled, argmax, Y):
+// the dense G is never materialised.  One 128-bit lane per 4 channels; M = B*L rows.
+__global__ void __launch_bounds__(256)
+segmax_bn_bwd_apply_kernel(const float* __restrict__ gp, int64_t ldg, const int* __restrict__ argmax,
+                           const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
+                           const float* __restrict__ shift, const float* __restrict__ mean,
+                           const float* __restrict__ var, float eps, int relu,
+                           const float* __restrict__ s1, const float* __restrict__ s2,
+                           float* __restrict__ dY, int64_t lddy, int64_t B, int L, int C) {
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + x) * 4;
+    if (c >= C) return;
+    const int64_t M = B * L;
+    float sc[4], sh[4], mu[4], rs[4], m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = scale[c + j];
+        sh[j] = shift[c + j];
+        mu[j] = mean[c + j];
+        rs[j] = 1.f / sqrtf(var[c + j] + eps);
+        m1[j] = s1[c + j] / (float)M;
+        m2[j] = s2[c + j] / (float)M;
+    }
+#pragma unroll 2
+    for (int64_t r = (int64_t)blockIdx.y * 8 + y; r < M; r += (int64_t)gridDim.y * 8) {
+        const int64_t b = r / L;
+        const int l = (int)(r - b * L);
+        const float4 yq = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
+        const int4 am = __ldg(reinterpret_cast<const int4*>(argmax + b * C + c));
+        const float4 gq = __ldg(reinterpret_cast<const float4*>(gp + b * ldg + c));
+        const float yv[4] = {yq.x, yq.y, yq.z, yq.w};
+        const int aq[4] = {am.x, am.y, am.z, am.w};
+        const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float g = (aq[j] == l) ? gv[j] : 0.f;
+            if (relu && !(fmaf(yv[j], sc[j], sh[j]) > 0.f)) g = 0.f;
+            d[j] = sc[j] * (g - m1[j] - (yv[j] - mu[j]) * rs[j] * m2[j]);
+        }
+        *reinterpret_cast<float4*>(dY + r * lddy + c) = make_float4(d[0], d[1], d[2], d[3]);
+    }
+}
+
+// out[c] = sum_k ws[k*C + c] in fp64, one warp per column (same as dense_vec.cu's merge).
+__global__ void __launch_bounds__(128)
+pool_colsum_merge_kernel(const float* __restrict__ ws, int64_t chunks, int C, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double a = 0.0;
+    for (int64_t k = lane; k < chunks; k += 32) a += (double)__ldg(ws + k * C + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[c] = (float)a;
+}
+
 __global__ void rows_scatter_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                     float* __restrict__ dst, int64_t n, int C) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +306,35 @@ int spg_segmax_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax, fl
     dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)gy);
     SPG_LAUNCH(K_SEGMAX_BWD, (cudaStream_t)stream, segmax_bwd_kernel, grid, 256, 0, g_pooled, ldg,
                argmax, G, ldG, rows, L, C);
+    return launch_status();
+}
+
+int spg_segmax_bn_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax, const float* Y,
+                      int64_t ldy, const float* scale, const float* shift, const float* mean,
+                      const float* var, float eps, int relu, float* s12, float* dY, int64_t lddy,
+                      float* workspace, int64_t B, int L, int C, spg_stream_t stream) {
+    if (B <= 0 || L <= 0 || C <= 0 || !g_pooled || !argmax || !Y || !scale || !shift || !mean || !var ||
+        !s12 || !dY || !workspace)
+        return SPG_E_BADARG;
+    if ((C & 3) || (ldg & 3) || (ldy & 3) || (lddy & 3)) return SPG_E_UNSUPPORTED;
+    if (((uintptr_t)g_pooled | (uintptr_t)argmax | (uintptr_t)Y | (uintptr_t)dY) & 15) return SPG_E_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t chunks = ceil_div64(B, 256);
+    if (chunks > 65535) return SPG_E_UNSUPPORTED;
+    dim3 g1((unsigned)ceil_div64(C, 32), (unsigned)chunks);
+    SPG_LAUNCH(K_SEGMAX_BWD, s, segmax_bn_bwd_reduce_kernel, g1, 256, 0, g_pooled, ldg, argmax, Y, ldy,
+               scale, shift, mean, var, eps, relu, workspace, B, L, C);
+    int rc = launch_status();
+    if (rc) return rc;
+    SPG_LAUNCH(K_SEGMAX_BWD, s, pool_colsum_merge_kernel, (unsigned)ceil_div64(2 * C, 4), 128, 0, workspace,
+               chunks, 2 * C, s12);
+    rc = launch_status();
+    if (rc) return rc;
+    int64_t gy = ceil_div64(B * L, 32);
+    if (gy > 16 * kNumSMs) gy = 16 * kNumSMs;
+    dim3 g2((unsigned)ceil_div64(C, 128), (unsigned)gy);
+    SPG_LAUNCH(K_SEGMAX_BWD, s, segmax_bn_bwd_apply_kernel, g2, 256, 0, g_pooled, ldg, argmax, Y, ldy, scale,
+               shift, mean, var, eps, relu, s12, s12 + C, dY, lddy, B, L, C);
     return launch_status();
 }
 

@@ -161,7 +161,7 @@ def chain_forward(inp, M, specs, params, training, saved=None):
     return cur
 
 
-def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_g=False):
+def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_g=False, pooled=None):
     """G: gradient w.r.t. the chain's final *activated* output [M, C_last].
     `grads` (list aligned with params) is filled in place.  Returns the gradient w.r.t. the
     chain input's activated value [M, cin_0] (or None)."""
@@ -169,7 +169,21 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
         sp = specs[li]
         cur, nxt, mean, var = saved[li]
         C = sp.cout
-        if sp.bn is not None:
+        fused_pool = (pooled is not None and li == len(specs) - 1 and sp.bn is not None
+                      and mean is not None and C % 4 == 0)
+        if G is None and not fused_pool:  # generic path: materialise the dense pooled gradient
+            gp, ldgp, argmax, Bc, Lc = pooled
+            G, ldg, own_g = ops.segmax_bwd(gp, ldgp, argmax, Bc, Lc, C), C, True
+        if fused_pool:
+            # the chain's output went through a max-pool: fused pool-backward + BN/ReLU backward
+            gp, ldgp, argmax, Bc, Lc = pooled
+            s1, s2, dY = ops.segmax_bn_bwd(gp, ldgp, argmax, nxt.raw, nxt.ld, nxt.scale, nxt.shift,
+                                           mean, var, sp.bn.eps, nxt.relu, Bc, Lc, C)
+            if sp.gamma is not None:
+                grads[sp.gamma] = s2
+                grads[sp.beta] = s1
+            ldy = C
+        elif sp.bn is not None:
             eps = sp.bn.eps
             s1, s2 = ops.act_bwd_reduce(G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var,
                                         eps, nxt.relu, M, C)

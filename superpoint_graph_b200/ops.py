@@ -392,6 +392,18 @@ def segmax_bwd(g_pooled, ldg, argmax, B, L, C):
     return G
 
 
+def segmax_bn_bwd(g_pooled, ldg, argmax, Y, ldy, scale, shift, mean, var, eps, relu, B, L, C):
+    """Fused max-pool backward + BatchNorm/ReLU backward; returns (s1, s2, dY[B*L, C])."""
+    _need_cuda(g_pooled, argmax, Y)
+    dev = Y.device
+    s12 = torch.empty(2 * C, dtype=torch.float32, device=dev)
+    dY = torch.empty((B * L, C), dtype=torch.float32, device=dev)
+    ws = workspace(2 * C * ((B + 255) // 256), dev)
+    _lib.call("spg_segmax_bn_bwd", g_pooled, ldg, argmax, Y, ldy, scale, shift, mean, var, float(eps),
+              int(bool(relu)), s12, dY, C, ws, B, L, C, _lib.current_stream())
+    return s12[:C], s12[C:], dY
+
+
 def stn_apply_bwd(clouds, dXrows, ld):
     _need_cuda(clouds, dXrows)
     clouds = _c(clouds)

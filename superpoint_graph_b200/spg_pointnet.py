@@ -108,8 +108,8 @@ def _stn_backward(dT, B, L, groups, params, saved, grads):
     cs, fs = groups
     Cs = saved["stn_Cs"]
     g_pool = chain_backward(dT, dT.shape[1], B, fs, params, saved["stn_f"], True, grads)
-    G = ops.segmax_bwd(g_pool, Cs, saved["stn_argmax"], B, L, Cs)
-    chain_backward(G, Cs, B * L, cs, params, saved["stn_c"], False, grads, own_g=True)
+    chain_backward(None, Cs, B * L, cs, params, saved["stn_c"], False, grads,
+                   pooled=(g_pool, Cs, saved["stn_argmax"], B, L))
 
 
 class _StnFunction(torch.autograd.Function):
@@ -266,10 +266,9 @@ class _PointNetFunction(torch.autograd.Function):
         gy = gy.contiguous()
         Ct, ld = saved["Ct"], saved["ld"]
         g_pool = chain_backward(gy, gy.shape[1], B, fc_g, params, saved["fc"], True, grads)
-        Gt = ops.segmax_bwd(g_pool, g_pool.shape[1], saved["argmax"], B, L, Ct)
+        g_rows = chain_backward(None, Ct, B * L, conv_g, params, saved["conv"], nfeat_stn > 0, grads,
+                                pooled=(g_pool, g_pool.shape[1], saved["argmax"], B, L))
         del g_pool
-        g_rows = chain_backward(Gt, Ct, B * L, conv_g, params, saved["conv"], nfeat_stn > 0, grads,
-                                own_g=True)
         if nfeat_stn > 0:
             dT = ops.stn_apply_bwd(ctx.clouds, g_rows, g_rows.shape[1])
             del g_rows

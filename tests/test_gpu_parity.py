@@ -504,3 +504,57 @@ def test_cuda_graph_replay_matches_eager(dev):
     close(torch.tensor(l_g[1:]), torch.tensor(l_e[1:]), 1e-5)
     close(o_g, o_e, 1e-4)
     close(p_g, p_e, 1e-4, 2.1e-2 * 4)  # noise-driven (pre-BN bias) parameters random-walk by +-lr
+
+
+def test_eval_chunking_matches_unchunked(dev, monkeypatch):
+    """Eval-mode PointNet slices huge inputs (Semantic3D-scale inference, configs[2]); BatchNorm in
+    eval mode is per-sample, so slicing must not change anything."""
+    from superpoint_graph_b200 import spg_pointnet
+    net = spg_pointnet.PointNet([64, 64, 128, 128, 256], [256, 64, 32], [64, 64, 128], [128, 64], 11, 11, prelast_do=0)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        net.stn.proj.weight.normal_(0, 0.05)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    B = 301
+    x, xg = torch.randn(B, 11, 128) * 0.4, torch.rand(B) * 3
+    pcfg = dict(n_conv=5, n_fc=3, n_conv_stn=3, n_fc_stn=2, nfeat_stn=11)
+    ref = nets_ref.pointnet_forward(x, xg, sd, pcfg, False)
+    net.to(dev).eval()
+    with torch.no_grad():
+        whole = net(x.to(dev), xg.to(dev))
+        monkeypatch.setattr(spg_pointnet, "_EVAL_CHUNK", 64)
+        sliced = net(x.to(dev), xg.to(dev))
+    close(whole, ref)
+    close(sliced, ref)
+    assert torch.equal(whole, sliced)
+
+
+def test_local_cloud_embedder_tiny_clouds(dev):
+    """Learned-partition embedder (configs[3] first half, pointnet.py:182-207): external STN on 2
+    features, 20-point clouds, global features + flattened T, L2-normalised 4-D output."""
+    from types import SimpleNamespace
+    from superpoint_graph_b200.spg_pointnet import LocalCloudEmbedder, PointNet, STNkD
+    torch.manual_seed(4)
+    model = torch.nn.Module()
+    model.stn = STNkD(2, [16, 64], [32, 16])
+    model.ptn = PointNet([32, 128], [34, 32, 32, 4], [], [], 6, 0, prelast_do=0, nfeat_global=11 + 4)
+    with torch.no_grad():
+        model.stn.proj.weight.normal_(0, 0.1)
+    sd_stn = {k: v.clone() for k, v in model.stn.state_dict().items()}
+    sd_ptn = {k: v.clone() for k, v in model.ptn.state_dict().items()}
+    B, L = 700, 20
+    clouds, glob = torch.randn(B, 6, L) * 0.5, torch.randn(B, 11)
+    T = nets_ref.stn_forward(clouds[:, :2], sd_stn, "", 2, 2, True)
+    xy = torch.bmm(clouds[:, :2].transpose(1, 2), T).transpose(1, 2)
+    c2 = torch.cat([xy, clouds[:, 2:]], 1)
+    g2 = torch.cat([glob, T.view(-1, 4)], 1)
+    pcfg = dict(n_conv=2, n_fc=4, n_conv_stn=0, n_fc_stn=0, nfeat_stn=0)
+    ref = torch.nn.functional.normalize(nets_ref.pointnet_forward(c2, g2, sd_ptn, pcfg, True))
+    model.to(dev).train()
+    emb = LocalCloudEmbedder(SimpleNamespace(ptn_nfeat_stn=2, stn_as_global=1))
+    out = emb.run_batch(model, clouds.to(dev), glob.to(dev))
+    close(out, ref, 2e-4)
