@@ -206,10 +206,11 @@ segmax_bn_bwd_apply_kernel(const float* __restrict__ gp, int64_t ldg, const int*
         const int l = (int)(r - b * L);
         const float4 yq = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
         const int4 am = __ldg(reinterpret_cast<const int4*>(argmax + b * C + c));
-        const float4 gq = __ldg(reinterpret_cast<const float4*>(gp + b * ldg + c));
+        // the pooled gradient row may be unaligned (ld = 256 + #global features): scalar loads, L1 hits
+        const float* gr = gp + b * ldg + c;
+        const float gv[4] = {__ldg(gr), __ldg(gr + 1), __ldg(gr + 2), __ldg(gr + 3)};
         const float yv[4] = {yq.x, yq.y, yq.z, yq.w};
         const int aq[4] = {am.x, am.y, am.z, am.w};
-        const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
         float d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -316,8 +317,8 @@ int spg_segmax_bn_bwd(const float* g_pooled, int64_t ldg, const int32_t* argmax,
     if (B <= 0 || L <= 0 || C <= 0 || !g_pooled || !argmax || !Y || !scale || !shift || !mean || !var ||
         !s12 || !dY || !workspace)
         return SPG_E_BADARG;
-    if ((C & 3) || (ldg & 3) || (ldy & 3) || (lddy & 3)) return SPG_E_UNSUPPORTED;
-    if (((uintptr_t)g_pooled | (uintptr_t)argmax | (uintptr_t)Y | (uintptr_t)dY) & 15) return SPG_E_ALIGN;
+    if ((C & 3) || (ldy & 3) || (lddy & 3)) return SPG_E_UNSUPPORTED;
+    if (((uintptr_t)argmax | (uintptr_t)Y | (uintptr_t)dY) & 15) return SPG_E_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t chunks = ceil_div64(B, 256);
     if (chunks > 65535) return SPG_E_UNSUPPORTED;
