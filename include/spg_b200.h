@@ -155,6 +155,9 @@ int spg_colstats_merge(float* partials, int64_t n_partials, int C, float* mean, 
 int64_t spg_tc_weight_image_floats(int N, int K);
 int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, int k_valid,
                         float* image, spg_stream_t stream);
+/* All weight images of a model in one launch: table (device, int64 [n_jobs,8]) rows are
+ * {W, ldw, transpose, N, K, k_valid, image, first element index}; total = sum N*K.            */
+int spg_tc_pack_weights_multi(const int64_t* table, int n_jobs, int64_t total, spg_stream_t stream);
 int spg_tc_gemm_supported(int64_t M, int N, int K);
 /* kernel generation (1: one CTA per tile; 2, default: persistent warp-specialised, resident weights)
  * and the number of statistics partials per column spg_tc_gemm writes for a given problem.     */

@@ -296,25 +296,36 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs p) {
     }
 }
 
-__global__ void gemm_splitk_reduce_kernel(const float* __restrict__ ws, int split, int64_t M,
-                                          int64_t N, const float* __restrict__ bias,
-                                          float* __restrict__ C, int64_t ldc) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * N) return;
-    const int64_t m = i / N, n = i % N;
-    float s = 0.f;
+// C[m,n] = sum_z ws[z,m,n] (+ bias[n]).  Block = 64 elements x 4 partial groups: every group sums a
+// strided quarter of the partials with 8 independent loads in flight, a fixed-order shared-memory
+// combine keeps the result deterministic.
+__global__ void __launch_bounds__(256)
+gemm_splitk_reduce_kernel(const float* __restrict__ ws, int split, int64_t M, int64_t N,
+                          const float* __restrict__ bias, float* __restrict__ C, int64_t ldc) {
+    __shared__ float part[4][64];
+    const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
+    const int64_t i = (int64_t)blockIdx.x * 64 + x;
     const int64_t stride = M * N;
-    int z = 0;
-    for (; z + 8 <= split; z += 8) {
-        float v[8];
+    float s = 0.f;
+    if (i < stride) {
+        int z = y;
+        for (; z + 28 < split; z += 32) {
+            float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (int64_t)(z + u) * stride + i);
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(ws + (int64_t)(z + 4 * u) * stride + i);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; z < split; z += 4) s += __ldg(ws + (int64_t)z * stride + i);
     }
-    for (; z < split; ++z) s += __ldg(ws + (int64_t)z * stride + i);
-    if (bias) s += bias[n];
-    C[m * ldc + n] = s;
+    part[y][x] = s;
+    __syncthreads();
+    if (y == 0 && i < stride) {
+        float t = (part[0][x] + part[1][x]) + (part[2][x] + part[3][x]);
+        const int64_t m = i / N, n = i % N;
+        if (bias) t += bias[n];
+        C[m * ldc + n] = t;
+    }
 }
 
 // ---------------------------------------------------------------- column reductions
@@ -663,7 +674,7 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
         if (rc) return rc;
     }
     if (split_k > 1) {
-        const int64_t blocks = ceil_div64(M * N, 256);
+        const int64_t blocks = ceil_div64(M * N, 64);
         SPG_LAUNCH(K_GEMM_SPLITK_REDUCE, s, gemm_splitk_reduce_kernel, (unsigned)blocks, 256, 0,
                    workspace, split_k, M, N, bias, C, ldc);
         return launch_status();
@@ -675,7 +686,7 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
 int spg_splitk_reduce(const float* partials, int split, int64_t M, int64_t N, const float* bias,
                       float* C, int64_t ldc, spg_stream_t stream) {
     if (!partials || !C || split < 1 || M <= 0 || N <= 0 || ldc < N) return SPG_E_BADARG;
-    const int64_t blocks = ceil_div64(M * N, 256);
+    const int64_t blocks = ceil_div64(M * N, 64);
     SPG_LAUNCH(K_GEMM_SPLITK_REDUCE, (cudaStream_t)stream, gemm_splitk_reduce_kernel,
                (unsigned)blocks, 256, 0, partials, split, M, N, bias, C, ldc);
     return launch_status();

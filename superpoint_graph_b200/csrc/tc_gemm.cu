@@ -46,6 +46,33 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int64_t ldw,
     img[base + (int64_t)N * TC_KC + off] = __uint_as_float(lo);
 }
 
+// Batched variant: one launch packs every weight matrix of a model (forward images and the
+// transposed images of the data-gradient GEMMs).  table[j] = {W, ldw, transpose, N, K, k_valid,
+// image, first element index of job j}; a thread finds its job by a linear scan (<= 64 jobs).
+__global__ void tc_pack_weights_multi_kernel(const long long* __restrict__ table, int n_jobs,
+                                             long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int j = 0;
+    while (j + 1 < n_jobs && i >= table[(j + 1) * 8 + 7]) ++j;
+    const long long* d = table + j * 8;
+    const float* W = reinterpret_cast<const float*>(d[0]);
+    const long long ldw = d[1];
+    const int transpose = (int)d[2], N = (int)d[3], K = (int)d[4], k_valid = (int)d[5];
+    float* img = reinterpret_cast<float*>(d[6]);
+    const long long e = i - d[7];
+    const int n = (int)(e / K), k = (int)(e % K);
+    float v = 0.f;
+    if (k < k_valid) v = transpose ? W[(long long)k * ldw + n] : W[(long long)n * ldw + k];
+    const uint32_t hi = to_tf32(v);
+    const uint32_t lo = to_tf32(v - __uint_as_float(hi));
+    const int kc = k / TC_KC, kk = k % TC_KC;
+    const long long base = (long long)kc * 2 * N * TC_KC;
+    const long long off = (long long)(sw128_off(n, kk >> 2) >> 2) + (kk & 3);
+    img[base + off] = __uint_as_float(hi);
+    img[base + (long long)N * TC_KC + off] = __uint_as_float(lo);
+}
+
 struct TcArgs {
     const float* A;
     int64_t lda;
@@ -274,6 +301,14 @@ int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K
     const int64_t total = (int64_t)N * K;
     SPG_LAUNCH(K_TC_PACK, (cudaStream_t)stream, tc_pack_weights_kernel,
                (unsigned)ceil_div64(total, 256), 256, 0, W, ldw, transpose, N, K, k_valid, image);
+    return launch_status();
+}
+
+int spg_tc_pack_weights_multi(const int64_t* table, int n_jobs, int64_t total, spg_stream_t stream) {
+    if (!table || n_jobs <= 0 || n_jobs > 64 || total <= 0) return SPG_E_BADARG;
+    SPG_LAUNCH(K_TC_PACK, (cudaStream_t)stream, tc_pack_weights_multi_kernel,
+               (unsigned)ceil_div64(total, 256), 256, 0, (const long long*)table, n_jobs,
+               (long long)total);
     return launch_status();
 }
 

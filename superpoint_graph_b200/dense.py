@@ -231,6 +231,22 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
     return G
 
 
+def pack_jobs(specs, params, M, ld_in, need_input_grad):
+    """Weight images a chain over M rows will ask for (same selection rules as chain_forward /
+    chain_backward), as jobs for ops.prepack."""
+    jobs = []
+    ld = ld_in
+    for li, sp in enumerate(specs):
+        W = _w2d(params[sp.w])
+        kpad = _padded_k(sp.cin, ld)
+        if ops.tc_supported(M, sp.cout, kpad, ld, sp.cout):
+            jobs.append((W, sp.cin, False, sp.cout, kpad, sp.cin))
+        if (li > 0 or need_input_grad) and ops.tc_supported(M, sp.cin, sp.cout, sp.cout, sp.cin):
+            jobs.append((W, sp.cin, True, sp.cin, sp.cout, sp.cout))
+        ld = sp.cout
+    return jobs
+
+
 class ChainFunction(torch.autograd.Function):
     """autograd wrapper: y = chain(x) with the final activation materialised."""
 

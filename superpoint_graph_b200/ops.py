@@ -254,14 +254,45 @@ def tc_supported(M, N, K, lda=0, ldc=0):
             and bool(_lib.lib().spg_tc_gemm_supported(int(M), int(N), int(K))))
 
 
+PACK_CACHE = {}   # (W ptr, ldw, transpose, N, K, k_valid) -> image, valid until the weights change
+_PACK_TABLES = {}  # tuple of job keys -> (device table, images, total)
+
+
+def prepack(jobs):
+    """Packs the weight images of many layers with ONE launch and publishes them in PACK_CACHE.
+    jobs: [(W, ldw, transpose, N, K, k_valid)].  The caller clears PACK_CACHE when the weights
+    change (Trainer does after every backward)."""
+    if not jobs:
+        return
+    keys = tuple((W.data_ptr(), int(ldw), int(bool(tr)), int(N), int(K), int(kv)) for W, ldw, tr, N, K, kv in jobs)
+    ent = _PACK_TABLES.get(keys)
+    dev = jobs[0][0].device
+    if ent is None:
+        rows, imgs, total = [], [], 0
+        for (ptr, ldw, tr, N, K, kv) in keys:
+            img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
+            imgs.append(img)
+            rows.append([ptr, ldw, tr, N, K, kv, img.data_ptr(), total])
+            total += N * K
+        table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        ent = _PACK_TABLES[keys] = (table, imgs, total)
+    table, imgs, total = ent
+    _lib.call("spg_tc_pack_weights_multi", table, len(keys), total, _lib.current_stream())
+    for k, img in zip(keys, imgs):
+        PACK_CACHE[k] = img
+
+
 def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False, k_valid=None):
     """C[M,N] = f(A)[M,K] B[N,K]^T + bias on the tcgen05 3xTF32 kernel.
     transpose=False: B = W ([N,K], ld ldw); True: B = W^T with W [K,N]."""
     _need_cuda(A, W)
     dev = A.device
-    img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
-    _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K,
-              int(K if k_valid is None else k_valid), img, _lib.current_stream())
+    kv = int(K if k_valid is None else k_valid)
+    img = PACK_CACHE.get((W.data_ptr(), int(ldw), int(bool(transpose)), int(N), int(K), kv))
+    if img is None:
+        img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
+        _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, kv, img,
+                  _lib.current_stream())
     out = torch.empty((M, N), dtype=torch.float32, device=dev)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
     tiles = int(_lib.lib().spg_tc_gemm_stats_partials(int(M), int(N), int(K)))

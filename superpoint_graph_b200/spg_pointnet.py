@@ -210,6 +210,20 @@ class PointNet(nn.Module):
                                        training, *params)
 
 
+def prepack_weights(ptn, n_clouds, n_points):
+    """One launch that builds every tensor-core weight image the next training forward+backward of
+    `ptn` on [n_clouds, F, n_points] will use (called by the Trainer at the start of a step)."""
+    from .dense import pack_jobs
+
+    M = n_clouds * n_points
+    stn_g, conv_g, fc_g, params = ptn._groups(True)
+    ld = _row_ld(ptn._nfeat)
+    jobs = pack_jobs(conv_g, params, M, ld, ptn.nfeat_stn > 0)
+    if stn_g is not None:
+        jobs += pack_jobs(stn_g[0], params, M, ld, False)
+    ops.prepack(jobs)
+
+
 _EVAL_CHUNK = 16384  # clouds per eval-mode slice (bounds the [B*L, 256] activation to 2 GB)
 
 

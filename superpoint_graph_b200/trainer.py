@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import ops
 from .spg_ecc import GraphConvInfo
 from .spg_graphnet import GraphNetwork
-from .spg_pointnet import CloudEmbedder, PointNet
+from .spg_pointnet import CloudEmbedder, PointNet, prepack_weights
 
 S3DIS_ARGS = dict(
     model_config="gru_10_1_1_1_0,f_13", ptn_widths=[[64, 64, 128, 128, 256], [256, 64, 32]],
@@ -145,10 +145,12 @@ class Trainer(object):
         self.model.train()
         for p in self.params:
             p.grad = None
+        prepack_weights(self.model.ptn, db.clouds.shape[0], db.clouds.shape[2])
         logits = self.forward(db)
         loss, d_logits = ops.ce_loss(logits, db.labels, self.class_weights, -100)
         logits.backward(d_logits)
         self.embedder.bw_hook()
+        ops.PACK_CACHE.clear()  # the optimizer is about to change the weights
         torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_grad)
         return loss, logits.detach()
 
