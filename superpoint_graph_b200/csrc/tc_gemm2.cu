@@ -25,8 +25,8 @@ namespace spg {
 
 constexpr int T2_BM = 128;
 constexpr int T2_KC = 32;
-constexpr int T2_STAGES = 2;
-constexpr int T2_EPI_WARPS = 4, T2_PROD_WARPS = 8;
+constexpr int T2_MAX_STAGES = 4;  // the A ring gets as many stages as fit next to the resident weights
+constexpr int T2_EPI_WARPS = 4, T2_PROD_WARPS = 8;  // (8 epilogue warps force 96 regs/thread: measured slower)
 constexpr int T2_THREADS = (T2_EPI_WARPS + 1 + T2_PROD_WARPS) * 32;  // 416
 constexpr int T2_A_BYTES = T2_BM * T2_KC * 4;                        // 16 KB (hi or lo)
 constexpr int T2_STAGE_BYTES = 2 * T2_A_BYTES;
@@ -43,6 +43,7 @@ struct Tc2Args {
     const float *a_scale, *a_shift;
     int a_relu;
     float* stats;  // [4*tiles, N, 3] or null
+    int nstages;   // A-ring depth (2..4)
     int dbg;       // experiment switches (SPG_TC_DBG): 1 no epilogue stores, 2 no MMA, 4 no loads, 8 no STS
 };
 
@@ -53,8 +54,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <int NS>
 __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[2 * T2_STAGES + 4];
+    // the dynamic segment starts 1024-byte aligned (declared alignment; static data is padded up to
+    // it): SWIZZLE_128B atoms need that, and no spare bytes are reserved for a manual round-up
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    __shared__ __align__(8) uint64_t bars[2 * T2_MAX_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
 
     const int t = threadIdx.x;
@@ -62,17 +66,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
     const int nk = p.K / T2_KC;
     const int n0 = blockIdx.y * NS;  // first output channel of this CTA's slice
     const int64_t tiles = (p.M + T2_BM - 1) / T2_BM;
-    uint8_t* wres = smem + T2_STAGES * T2_STAGE_BYTES;  // resident weights: [nk][hi|lo][NS][128 B]
+    const int nst = p.nstages;
+    uint8_t* wres = smem + (size_t)nst * T2_STAGE_BYTES;  // resident weights: [nk][hi|lo][NS][128 B]
 
     const uint32_t bars_u32 = smem_u32(&bars[0]);
     auto bar_full = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
-    auto bar_empty = [&](int s) { return bars_u32 + 8u * (uint32_t)(T2_STAGES + s); };
-    auto bar_accfull = [&](uint32_t a) { return bars_u32 + 8u * (2 * T2_STAGES + a); };
-    auto bar_accempty = [&](uint32_t a) { return bars_u32 + 8u * (2 * T2_STAGES + 2 + a); };
+    auto bar_empty = [&](int s) { return bars_u32 + 8u * (uint32_t)(T2_MAX_STAGES + s); };
+    auto bar_accfull = [&](uint32_t a) { return bars_u32 + 8u * (2 * T2_MAX_STAGES + a); };
+    auto bar_accempty = [&](uint32_t a) { return bars_u32 + 8u * (2 * T2_MAX_STAGES + 2 + a); };
 
     if (t == 0) {
 #pragma unroll
-        for (int s = 0; s < T2_STAGES; ++s) {
+        for (int s = 0; s < T2_MAX_STAGES; ++s) {
             mbar_init(bar_full(s), T2_PROD_WARPS);  // one elected arrival per producer warp
             mbar_init(bar_empty(s), 1);
         }
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
                          : "memory");
         };
         auto consume = [&](float4 (&cur)[4], float4 (&far)[4]) {
-            const int s = it % T2_STAGES;
-            const uint32_t use = it / T2_STAGES;
+            const int s = it % nst;
+            const uint32_t use = it / nst;
             load(ltile, lkc, far);  // item it+PF-1
             advance(ltile, lkc);
             const float4 sc = *reinterpret_cast<const float4*>(sc_s + kc * T2_KC + c16 * 4);
@@ -228,8 +233,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + a * NS;
                 for (int kc = 0; kc < nk; ++kc, ++it) {
-                    const int s = it % T2_STAGES;
-                    mbar_wait(bar_full(s), (it / T2_STAGES) & 1);
+                    const int s = it % nst;
+                    mbar_wait(bar_full(s), (it / nst) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * T2_STAGE_BYTES);
                     const uint32_t a_lo = a_hi + T2_A_BYTES;
@@ -253,7 +258,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
         }
     } else {
         // ================================ epilogue ================================
-        const int w = warp;  // 0..3 == TMEM lane quarter
+        const int w = warp & 3;      // TMEM lane quarter this warp may access
+        const int cb0 = warp >> 2;   // the two warps of a quarter take alternate 32-column blocks
         uint32_t tcount = 0;
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
             const uint32_t a = tcount & 1;
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
             const bool valid = row < p.M;
             const float nvalid = (float)max((int64_t)0, min((int64_t)32, p.M - row0));
 #pragma unroll 1
-            for (int cb = 0; cb < NS / 32; ++cb) {
+            for (int cb = cb0; cb < NS / 32; cb += T2_EPI_WARPS / 4) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * NS + cb * 32), r);
                 const int col0 = n0 + cb * 32;
@@ -339,12 +345,17 @@ static int launch_tc2(const Tc2Args& a, cudaStream_t s) {
     int64_t gx = kNumSMs / slices;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;
-    const int smem = T2_STAGES * T2_STAGE_BYTES + (a.K / T2_KC) * 2 * NS * T2_KC * 4 +
-                     (2 * a.K + NS) * 4 + 1024;
+    const int fixed = (a.K / T2_KC) * 2 * NS * T2_KC * 4 + (2 * a.K + NS) * 4;
+    int nst = (232448 - 1024 - fixed) / T2_STAGE_BYTES;  // 227 KB per CTA minus 1 KB static
+    if (nst > T2_MAX_STAGES) nst = T2_MAX_STAGES;
+    if (nst < 2) return SPG_E_UNSUPPORTED;
+    Tc2Args a2 = a;
+    a2.nstages = nst;
+    const int smem = nst * T2_STAGE_BYTES + fixed;
     cudaError_t e = cudaFuncSetAttribute(tc_gemm2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    SPG_LAUNCH(K_TC_GEMM, s, tc_gemm2_kernel<NS>, grid, T2_THREADS, smem, a);
+    SPG_LAUNCH(K_TC_GEMM, s, tc_gemm2_kernel<NS>, grid, T2_THREADS, smem, a2);
     return launch_status();
 }
 
