@@ -101,7 +101,18 @@ def call(name, *args):
         raise RuntimeError("%s failed: [%d] %s" % (name, rc, error_string(rc)))
 
 
-def current_stream():
-    import torch
+_raw_stream = None
 
-    return torch.cuda.current_stream().cuda_stream
+
+def current_stream():
+    """Raw cudaStream_t (int) of torch's current stream on the current device."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+
+        getter = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if getter is not None:
+            _raw_stream = lambda: getter(torch.cuda.current_device())
+        else:
+            _raw_stream = lambda: torch.cuda.current_stream().cuda_stream
+    return _raw_stream()

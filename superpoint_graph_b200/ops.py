@@ -40,7 +40,7 @@ _workspaces = {}
 
 def workspace(nfloats, device):
     """Per (device, stream) scratch buffer; stream order makes reuse across calls safe."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, _lib.current_stream())
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nfloats:
         buf = torch.empty(max(int(nfloats), 1 << 16), dtype=torch.float32, device=device)
