@@ -558,3 +558,56 @@ def test_local_cloud_embedder_tiny_clouds(dev):
     emb = LocalCloudEmbedder(SimpleNamespace(ptn_nfeat_stn=2, stn_as_global=1))
     out = emb.run_batch(model, clouds.to(dev), glob.to(dev))
     close(out, ref, 2e-4)
+
+
+def test_cloud_embedder_mem_monger_same_gradients(dev):
+    """ptn_mem_monger=1 (no-grad forward + full recomputation in bw_hook, pointnet.py:160-180) must
+    give the gradients of the plain path; only the running statistics see two updates per step."""
+    from superpoint_graph_b200.synthetic import make_batch
+    from superpoint_graph_b200.trainer import HostBatch, Trainer, create_model, make_args
+    batch = make_batch(n_nodes=150, seed=21)
+    grads = []
+    for monger in (0, 1):
+        args = make_args(model_config="gru_2_1_1_1_0,f_13", ptn_mem_monger=monger)
+        torch.manual_seed(9)
+        model = create_model(args)
+        model.to(dev)
+        tr = Trainer(model, args)
+        db = HostBatch(batch).to_device(dev)
+        # CloudEmbedder API as main.py:202-208 drives it
+        model.train()
+        model.ecc.gconvs[0].set_info(db.gi)
+        emb = tr.embedder.run(model, None, batch["clouds_flag"], batch["clouds"], batch["clouds_global"])
+        out = model.ecc(emb)
+        loss = torch.nn.functional.cross_entropy(out, db.labels)
+        loss.backward()
+        tr.embedder.bw_hook()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    close_grads(grads[1], grads[0], 1e-5)
+
+
+def test_graph_conv_module_matrix_filters(dev):
+    """ecc.GraphConvModule (GraphConvModule.py:156-193): filter net -> [E,in,out] -> function."""
+    from superpoint_graph_b200.spg_ecc import GraphConvInfo, GraphConvModule
+    from superpoint_graph_b200.spg_graphnet import create_fnet
+    rng = np.random.default_rng(2)
+    N, cin, cout = 90, 8, 12
+    degs_np = rng.integers(0, 6, size=N)
+    E = int(degs_np.sum())
+    idxn = rng.integers(0, N, size=E)
+    ef = rng.standard_normal((E, 5)).astype(np.float32)
+    torch.manual_seed(2)
+    fnet = create_fnet([5, 16, cin * cout], True, True)
+    sd = {k: v.clone().requires_grad_(True) for k, v in fnet.state_dict().items()}
+    x = torch.randn(N, cin)
+    w_ref = nets_ref.fnet_forward(t(ef), sd, "", [5, 16, cin * cout], -1, True).view(E, cin, cout)
+    ref = ecc_ref.graph_conv_forward(x, w_ref, t(idxn), None, t(degs_np))
+    gout = torch.randn(N, cout)
+    ref.backward(gout)
+    mod = GraphConvModule(cin, cout, fnet, GraphConvInfo.from_arrays(idxn, degs_np, ef)).to(dev).train()
+    mod._gci.cuda()
+    xg = x.to(dev).requires_grad_(True)
+    out = mod(xg)
+    close(out, ref)
+    out.backward(gout.to(dev))
+    close_grads({k: p.grad for k, p in fnet.named_parameters()}, {k: v.grad for k, v in sd.items()}, 3e-4)
