@@ -141,6 +141,12 @@ int spg_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t 
 int64_t spg_gemm_stats_tiles(int64_t M);
 int spg_colstats_merge(float* partials, int64_t n_partials, int C, float* mean, float* var,
                        spg_stream_t stream);
+/* merge + spg_bn_fold in one pass (the last merge level folds): */
+int spg_colstats_merge_fold(float* partials, int64_t n_partials, int C, float* mean, float* var,
+                            const float* gamma, const float* beta, float eps, float* scale,
+                            float* shift, float* running_mean, float* running_var,
+                            int64_t* num_batches_tracked, float momentum, int64_t M,
+                            spg_stream_t stream);
 /* (the merge is two-level: `partials` needs room for ceil(n_partials/256) extra triples per column
  *  after the n_partials*C*3 floats; the same holds for the workspaces of spg_colstats / stats_ws) */
 

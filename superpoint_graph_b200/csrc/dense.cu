@@ -378,10 +378,19 @@ colstats_partial_kernel(const float* __restrict__ Y, int64_t ldy, int64_t M, int
 // the two passes); grid.y > 1 writes block-level partials (same triple format) for a second level.
 constexpr int kMergePerBlock = 256;
 
+// optional BatchNorm fold executed by the last merge level (saves a launch per layer)
+struct FoldArgs {
+    const float *gamma, *beta;
+    float *scale, *shift, *rmean, *rvar;
+    long long* nbt;
+    float eps, momentum, unbias;
+    int enabled;
+};
+
 __global__ void __launch_bounds__(1024)
 colstats_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
                       float* __restrict__ mean, float* __restrict__ var,
-                      float* __restrict__ out_partials) {
+                      float* __restrict__ out_partials, const FoldArgs f) {
     __shared__ double s_a[32][33], s_b[32][33];
     __shared__ double s_mean[32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -436,32 +445,59 @@ colstats_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
             o[1] = (float)mu;
             o[2] = (float)qq;
         } else {
-            mean[c] = (float)mu;
-            var[c] = ntot > 0.0 ? (float)(qq / ntot) : 0.f;
+            const float mu_f = (float)mu;
+            const float var_f = ntot > 0.0 ? (float)(qq / ntot) : 0.f;
+            mean[c] = mu_f;
+            var[c] = var_f;
+            if (f.enabled) {
+                const float rstd = 1.f / sqrtf(var_f + f.eps);
+                const float sc = (f.gamma ? f.gamma[c] : 1.f) * rstd;
+                f.scale[c] = sc;
+                f.shift[c] = (f.beta ? f.beta[c] : 0.f) - mu_f * sc;
+                if (f.rmean) f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * mu_f;
+                if (f.rvar) f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * var_f * f.unbias;
+                if (c == 0 && f.nbt) f.nbt[0] += 1;
+            }
         }
     }
 }
 
 // two-level driver; `partials` must have room for ceil(n/256) extra triples per column at its end
 static int colstats_merge_launch(float* partials, int64_t n, int C, float* mean, float* var,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, const FoldArgs& fold) {
+    FoldArgs nofold;
+    nofold.enabled = 0;
+    nofold.gamma = nofold.beta = nullptr;
+    nofold.scale = nofold.shift = nofold.rmean = nofold.rvar = nullptr;
+    nofold.nbt = nullptr;
+    nofold.eps = nofold.momentum = nofold.unbias = 0.f;
     const unsigned gx = (unsigned)ceil_div64(C, 32);
     const int64_t P = ceil_div64(n, kMergePerBlock);
     if (P > 65535) return SPG_E_UNSUPPORTED;
     if (P == 1) {
         SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, dim3(gx, 1), 1024, 0, partials, n, C,
-                   mean, var, (float*)nullptr);
+                   mean, var, (float*)nullptr, fold);
         return launch_status();
     }
     float* lvl2 = partials + n * C * 3;
     SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, dim3(gx, (unsigned)P), 1024, 0, partials, n,
-               C, mean, var, lvl2);
+               C, mean, var, lvl2, nofold);
     int rc = launch_status();
     if (rc) return rc;
     if (P > kMergePerBlock) return SPG_E_UNSUPPORTED;
     SPG_LAUNCH(K_COLSTATS_FINAL, s, colstats_final_kernel, dim3(gx, 1), 1024, 0, lvl2, P, C, mean, var,
-               (float*)nullptr);
+               (float*)nullptr, fold);
     return launch_status();
+}
+
+static FoldArgs no_fold() {
+    FoldArgs f;
+    f.enabled = 0;
+    f.gamma = f.beta = nullptr;
+    f.scale = f.shift = f.rmean = f.rvar = nullptr;
+    f.nbt = nullptr;
+    f.eps = f.momentum = f.unbias = 0.f;
+    return f;
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
@@ -706,7 +742,7 @@ int spg_colstats(const float* Y, int64_t ldy, int64_t M, int C, float* mean, flo
                workspace);
     int rc = launch_status();
     if (rc) return rc;
-    return colstats_merge_launch(workspace, chunks, C, mean, var, s);
+    return colstats_merge_launch(workspace, chunks, C, mean, var, s, no_fold());
 }
 
 int64_t spg_gemm_stats_tiles(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, BM); }
@@ -714,7 +750,22 @@ int64_t spg_gemm_stats_tiles(int64_t M) { return M <= 0 ? 1 : ceil_div64(M, BM);
 int spg_colstats_merge(float* partials, int64_t n_partials, int C, float* mean, float* var,
                        spg_stream_t stream) {
     if (n_partials <= 0 || C <= 0 || !partials || !mean || !var) return SPG_E_BADARG;
-    return colstats_merge_launch(partials, n_partials, C, mean, var, (cudaStream_t)stream);
+    return colstats_merge_launch(partials, n_partials, C, mean, var, (cudaStream_t)stream, no_fold());
+}
+
+int spg_colstats_merge_fold(float* partials, int64_t n_partials, int C, float* mean, float* var,
+                            const float* gamma, const float* beta, float eps, float* scale,
+                            float* shift, float* running_mean, float* running_var,
+                            int64_t* num_batches_tracked, float momentum, int64_t M,
+                            spg_stream_t stream) {
+    if (n_partials <= 0 || C <= 0 || !partials || !mean || !var || !scale || !shift) return SPG_E_BADARG;
+    FoldArgs f;
+    f.enabled = 1;
+    f.gamma = gamma; f.beta = beta; f.scale = scale; f.shift = shift;
+    f.rmean = running_mean; f.rvar = running_var; f.nbt = (long long*)num_batches_tracked;
+    f.eps = eps; f.momentum = momentum;
+    f.unbias = M > 1 ? (float)((double)M / (double)(M - 1)) : 1.f;
+    return colstats_merge_launch(partials, n_partials, C, mean, var, (cudaStream_t)stream, f);
 }
 
 int spg_bn_fold(const float* mean, const float* var, const float* gamma, const float* beta,

@@ -127,30 +127,35 @@ def chain_forward(inp, M, specs, params, training, saved=None):
         bias = params[sp.b] if sp.b is not None else None
         bn = sp.bn
         batch_stats = bn is not None and (training or not bn.track_running_stats)
+        fold = None
+        if batch_stats:
+            # BatchNorm fold (scale/shift, running statistics, num_batches_tracked) rides on the last
+            # level of the statistics merge
+            rm = rv = nbt = None
+            mom = 0.0
+            if training and bn.track_running_stats:
+                rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+                if bn.momentum is None:
+                    raise NotImplementedError("BatchNorm momentum=None (cumulative average)")
+                mom = bn.momentum
+            fold = (params[sp.gamma] if sp.gamma is not None else None,
+                    params[sp.beta] if sp.beta is not None else None, bn.eps, rm, rv, nbt, mom)
         kpad = _padded_k(sp.cin, cur.ld)
         if ops.tc_supported(M, sp.cout, kpad, cur.ld, sp.cout) and (kpad == sp.cin or not cur.pending):
             # reduction dimension zero-padded to a multiple of 32 (the rows are zero-padded to
             # cur.ld and the weight image gets zeros there)
             res = ops.tc_gemm(cur.raw, cur.ld, W, sp.cin, False, M, sp.cout, kpad, bias=bias,
-                              a_aff=cur.aff(), stats=batch_stats, k_valid=sp.cin)
+                              a_aff=cur.aff(), stats=batch_stats, k_valid=sp.cin, fold=fold)
         else:
             res = ops.gemm(cur.raw, cur.ld, True, W, sp.cin, True, M, sp.cout, sp.cin, bias=bias,
-                           a_aff=cur.aff(), stats=batch_stats)
+                           a_aff=cur.aff(), stats=batch_stats, fold=fold)
         mean = var = scale = shift = None
         y = res
         if bn is not None:
             gamma = params[sp.gamma] if sp.gamma is not None else None
             beta = params[sp.beta] if sp.beta is not None else None
             if batch_stats:
-                y, mean, var = res  # batch statistics come fused out of the GEMM epilogue
-                rm = rv = nbt = None
-                mom = 0.0
-                if training and bn.track_running_stats:
-                    rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
-                    if bn.momentum is None:
-                        raise NotImplementedError("BatchNorm momentum=None (cumulative average)")
-                    mom = bn.momentum
-                scale, shift = ops.bn_fold(mean, var, gamma, beta, bn.eps, rm, rv, mom, M, nbt)
+                y, mean, var, scale, shift = res  # statistics + fold come out of the GEMM's merge
             else:
                 mean, var = bn.running_mean, bn.running_var
                 scale, shift = ops.bn_fold(mean, var, gamma, beta, bn.eps)

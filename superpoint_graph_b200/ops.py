@@ -209,8 +209,23 @@ def _auto_split(M, N, K):
     return max(1, split)
 
 
+def _merge_stats(sws, tiles, N, M, dev, fold):
+    """(mean, var) or, with fold=(gamma, beta, eps, rm, rv, nbt, momentum), (mean, var, scale, shift)."""
+    mean = torch.empty(N, dtype=torch.float32, device=dev)
+    var = torch.empty(N, dtype=torch.float32, device=dev)
+    if fold is None:
+        _lib.call("spg_colstats_merge", sws, tiles, N, mean, var, _lib.current_stream())
+        return mean, var
+    gamma, beta, eps, rm, rv, nbt, mom = fold
+    scale = torch.empty(N, dtype=torch.float32, device=dev)
+    shift = torch.empty(N, dtype=torch.float32, device=dev)
+    _lib.call("spg_colstats_merge_fold", sws, tiles, N, mean, var, gamma, beta, float(eps), scale, shift,
+              rm, rv, nbt, float(mom), int(M), _lib.current_stream())
+    return mean, var, scale, shift
+
+
 def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=None,
-         a_aff=None, b_aff=None, split_k=None, stats=False):
+         a_aff=None, b_aff=None, split_k=None, stats=False, fold=None):
     """C[M,N] = opA(A) opB(B) + bias.  a_aff/b_aff = (scale|None, shift|None, relu)."""
     _need_cuda(A, B)
     dev = A.device
@@ -239,10 +254,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
         GEMM_TRACE.append(("M=%d N=%d K=%d a%d b%d split=%d" % (M, N, K, int(a_kmajor), int(b_kmajor), split_k),
                            ev0, ev1))
     if stats:
-        mean = torch.empty(N, dtype=torch.float32, device=dev)
-        var = torch.empty(N, dtype=torch.float32, device=dev)
-        _lib.call("spg_colstats_merge", sws, tiles, N, mean, var, _lib.current_stream())
-        return out, mean, var
+        return (out,) + _merge_stats(sws, tiles, N, M, dev, fold)
     return out
 
 
@@ -282,7 +294,8 @@ def prepack(jobs):
         PACK_CACHE[k] = img
 
 
-def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False, k_valid=None):
+def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False, k_valid=None,
+            fold=None):
     """C[M,N] = f(A)[M,K] B[N,K]^T + bias on the tcgen05 3xTF32 kernel.
     transpose=False: B = W ([N,K], ld ldw); True: B = W^T with W [K,N]."""
     _need_cuda(A, W)
@@ -302,10 +315,7 @@ def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=Fal
     _lib.call("spg_tc_gemm", A, lda, img, bias, out, N, M, N, K, a_s, a_t, int(bool(a_r)), sws,
               _lib.current_stream())
     if stats:
-        mean = torch.empty(N, dtype=torch.float32, device=dev)
-        var = torch.empty(N, dtype=torch.float32, device=dev)
-        _lib.call("spg_colstats_merge", sws, tiles, N, mean, var, _lib.current_stream())
-        return out, mean, var
+        return (out,) + _merge_stats(sws, tiles, N, M, dev, fold)
     return out
 
 
