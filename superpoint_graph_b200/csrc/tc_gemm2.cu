@@ -30,6 +30,7 @@ constexpr int T2_EPI_WARPS = 4, T2_PROD_WARPS = 8;  // (8 epilogue warps force 9
 constexpr int T2_THREADS = (T2_EPI_WARPS + 1 + T2_PROD_WARPS) * 32;  // 416
 constexpr int T2_A_BYTES = T2_BM * T2_KC * 4;                        // 16 KB (hi or lo)
 constexpr int T2_STAGE_BYTES = 2 * T2_A_BYTES;
+constexpr int T2_EPI_PITCH = 36;  // floats per row of an epilogue transpose tile (16-byte aligned rows)
 
 struct Tc2Args {
     const float* A;
@@ -109,6 +110,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
     float* sc_s = reinterpret_cast<float*>(wres + (size_t)nk * 2 * NS * T2_KC * 4);
     float* sh_s = sc_s + p.K;
     float* bias_s = sh_s + p.K;
+    // per-epilogue-warp transpose tiles [32 rows][36]: accumulator rows (one per lane) are turned
+    // into full 128-byte lines before they go to global memory
+    float* epi_s = bias_s + NS;
     for (int i = t; i < p.K; i += T2_THREADS) {
         sc_s[i] = p.a_scale ? p.a_scale[i] : 1.f;
         sh_s[i] = p.a_shift ? p.a_shift[i] : 0.f;
@@ -278,48 +282,51 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     v[j] = __uint_as_float(r[j]) + bias_s[cb * 32 + j];
-                if (valid && !(p.dbg & 1)) {
-                    float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + col0);
+                if (!(p.dbg & 1)) {
+                    // lane = row -> shared tile -> (4 rows x 128 B) per store instruction
+                    float* tile_s = epi_s + warp * (32 * T2_EPI_PITCH);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        *reinterpret_cast<float4*>(tile_s + lane * T2_EPI_PITCH + 4 * j) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    const int rr = lane >> 3, c4 = lane & 7;
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int r = itr * 4 + rr;
+                        const float4 q = *reinterpret_cast<const float4*>(tile_s + r * T2_EPI_PITCH + 4 * c4);
+                        if (row0 + r < p.M)
+                            *reinterpret_cast<float4*>(p.C + (row0 + r) * p.ldc + col0 + 4 * c4) = q;
+                    }
+                    __syncwarp();
                 }
                 if (p.stats && !(p.dbg & 1)) {
-                    // pivoted sums over the 32 rows of this warp: d = v - v(row 0 of the group)
-                    float mypivot = 0.f;
-                    float d1[32], d2[32];
+                    // per-column sums over the 32 rows of this warp, read back from the transpose
+                    // tile (lane = column: conflict-free), pivoted on the group's first row
+                    const float* tile_c = epi_s + warp * (32 * T2_EPI_PITCH) + lane;
+                    // (the tile still holds this block: the stores above only read it)
+                    const float pivot = tile_c[0];
+                    float d1 = 0.f, d2 = 0.f;
+                    const int nv = (int)nvalid;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float pj = __shfl_sync(0xffffffffu, v[j], 0);
-                        if (lane == j) mypivot = pj;
-                        const float d = valid ? v[j] - pj : 0.f;
-                        d1[j] = d;
-                        d2[j] = d * d;
-                    }
-                    // transpose-reduce: afterwards lane j holds the column-j sums in d1[0], d2[0]
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                        for (int j = 0; j < off; ++j) {
-                            const bool up = lane & off;
-                            const float k1 = up ? d1[j + off] : d1[j];
-                            const float s1 = up ? d1[j] : d1[j + off];
-                            const float k2 = up ? d2[j + off] : d2[j];
-                            const float s2 = up ? d2[j] : d2[j + off];
-                            d1[j] = k1 + __shfl_xor_sync(0xffffffffu, s1, off);
-                            d2[j] = k2 + __shfl_xor_sync(0xffffffffu, s2, off);
+                    for (int r = 0; r < 32; ++r) {
+                        const float d = tile_c[r * T2_EPI_PITCH] - pivot;
+                        if (r < nv) {
+                            d1 += d;
+                            d2 = fmaf(d, d, d2);
                         }
                     }
                     float* o = p.stats + (((int64_t)tile * 4 + w) * p.N + col0 + lane) * 3;
                     if (nvalid > 0.f) {
                         o[0] = nvalid;
-                        o[1] = mypivot + d1[0] / nvalid;
-                        o[2] = fmaxf(d2[0] - d1[0] * d1[0] / nvalid, 0.f);
+                        o[1] = pivot + d1 / nvalid;
+                        o[2] = fmaxf(d2 - d1 * d1 / nvalid, 0.f);
                     } else {
                         o[0] = 0.f;
                         o[1] = 0.f;
                         o[2] = 0.f;
                     }
+                    __syncwarp();
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -345,7 +352,8 @@ static int launch_tc2(const Tc2Args& a, cudaStream_t s) {
     int64_t gx = kNumSMs / slices;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;
-    const int fixed = (a.K / T2_KC) * 2 * NS * T2_KC * 4 + (2 * a.K + NS) * 4;
+    const int fixed = (a.K / T2_KC) * 2 * NS * T2_KC * 4 + (2 * a.K + NS) * 4 +
+                      T2_EPI_WARPS * 32 * T2_EPI_PITCH * 4;
     int nst = (232448 - 1024 - fixed) / T2_STAGE_BYTES;  // 227 KB per CTA minus 1 KB static
     if (nst > T2_MAX_STAGES) nst = T2_MAX_STAGES;
     if (nst < 2) return SPG_E_UNSUPPORTED;
