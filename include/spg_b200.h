@@ -118,6 +118,36 @@ int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const floa
                 float* d_gi, float* d_gh, float* d_q, float* xprime, float* dpre,
                 int64_t n_rows, int hidden, int flags, spg_stream_t stream);
 
+/* ------------------------------------------- fused recurrence (R x {ECC, cell})
+ * The whole loop of RNNGraphConvModule.forward (ref: learning/modules.py:160-180:
+ * `for r: input = GraphConvFunction(hx, weights); hx = cell(input, hx)`) as ONE persistent
+ * kernel per direction, for vector filters ([n_edges,H]), H == 32, no idxe, and batches
+ * small enough that a warp per superpoint fills the GPU (spg_rnn_vv_supported).  A warp
+ * owns a node through all steps; steps are separated by a grid-wide barrier
+ * (barrier_ws: >= 4 bytes of device memory, zeroed by the call).
+ *   hs   [R+1,n,H]  hs[0] = initial state on entry; hs[1..R] written
+ *   inps [R,n,H]    ECC outputs of every step (kept for the backward)              */
+int spg_rnn_vv_supported(int64_t n_nodes, int hidden);
+int spg_rnn_vv_fwd(float* hs, float* inps, const float* w, const int32_t* tgt_rowptr,
+                   const int32_t* idxn, const float* weight_ih, const float* weight_hh,
+                   const float* bias_ih, const float* bias_hh, const float* ig_weight,
+                   const float* ig_bias, int64_t n_nodes, int hidden, int n_repeats, int flags,
+                   void* barrier_ws, spg_stream_t stream);
+/* Backward of the loop: grad_top [n,H] is the gradient w.r.t. hs[R]; grad_cat (NULL or
+ * [R+1,n,H]) the direct gradient of every hs[r] when all states were concatenated
+ * (`cat_all`, ref: modules.py:166,178; grad_top is then grad_cat[R]).  Outputs: grad_inp
+ * [R,n,H] (gradient of every ECC output, consumed by spg_ecc_bwd_w), grad_h0 [n,H], and the
+ * per-row parameter-gradient factors of spg_gru_bwd stacked over the steps
+ * (d_gi,d_gh [R,n,3H]; d_q,xprime [R,n,H]; dpre [R,n,4H]).  d_h_ws: [n,H] scratch.      */
+int spg_rnn_vv_bwd(const float* hs, const float* inps, const float* w, const float* grad_top,
+                   const float* grad_cat, const int32_t* tgt_rowptr, const int32_t* src_rowptr,
+                   const int32_t* src_perm, const int32_t* edge_tgt, const float* weight_ih,
+                   const float* weight_hh, const float* bias_ih, const float* bias_hh,
+                   const float* ig_weight, const float* ig_bias, float* grad_inp, float* d_h_ws,
+                   float* grad_h0, float* d_gi, float* d_gh, float* d_q, float* xprime,
+                   float* dpre, int64_t n_nodes, int hidden, int n_repeats, int flags,
+                   void* barrier_ws, spg_stream_t stream);
+
 /* ------------------------------------------------------------- dense      */
 /* C[M,N] = opA(A) * opB(B) (+ bias[N]), fp32, FMA accumulation.
  *   a_kmajor=1: A is [M,K] (ld = lda, K contiguous); 0: A is [K,M] (M contiguous)

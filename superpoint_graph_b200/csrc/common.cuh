@@ -43,6 +43,8 @@ enum KernelId {
     K_TC_GEMM,
     K_TC_PACK,
     K_TC_DW,
+    K_RNN_FWD,
+    K_RNN_BWD,
     K_COUNT
 };
 

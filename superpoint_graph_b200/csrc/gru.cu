@@ -46,8 +46,7 @@ __device__ __forceinline__ void gru_load_weights(float* sm, const float* __restr
 // gi/gh = raw (pre-norm) gate inputs, stats = {mean_i, rstd_i, mean_h, rstd_h}.
 template <int kRW>
 __device__ __forceinline__ void gru_rows_forward(const float* sm, float* scratch, int H, int flags,
-                                                 const float* __restrict__ x,
-                                                 const float* __restrict__ h,
+                                                 const float* x, const float* h,
                                                  const float* __restrict__ b_ig, int64_t row0,
                                                  int64_t n_rows, int lane, float stats[kRW][4]) {
     const float* Wig_t = sm;
@@ -142,6 +141,43 @@ __device__ __forceinline__ void gru_rows_forward(const float* sm, float* scratch
     }
 }
 
+// New hidden state of the RW rows whose gate inputs gru_rows_forward left in `scratch`.
+template <int kRW>
+__device__ __forceinline__ void gru_rows_emit(const float* scratch, int H, int flags,
+                                              const float* __restrict__ b_ih,
+                                              const float* __restrict__ b_hh, float* hy,
+                                              int64_t row0, int64_t n_rows, int lane,
+                                              const float st[kRW][4]) {
+    const float* hrow = scratch;
+    const float* gi = scratch + 3 * kRW * H;
+    const float* gh = gi + kRW * 3 * H;
+    const int H3 = 3 * H;
+    const bool has_bias = flags & SPG_GRU_BIAS;
+    for (int c = lane; c < H; c += 32) {
+        const float bir = has_bias ? b_ih[c] : 0.f, biz = has_bias ? b_ih[H + c] : 0.f,
+                    bin = has_bias ? b_ih[2 * H + c] : 0.f;
+        const float bhr = has_bias ? b_hh[c] : 0.f, bhz = has_bias ? b_hh[H + c] : 0.f,
+                    bhn = has_bias ? b_hh[2 * H + c] : 0.f;
+#pragma unroll
+        for (int i = 0; i < kRW; ++i) {
+            const int64_t row = row0 + i;
+            if (row >= n_rows) break;
+            const float i_r = (gi[i * H3 + c] - st[i][0]) * st[i][1];
+            const float i_z = (gi[i * H3 + H + c] - st[i][0]) * st[i][1];
+            const float i_n = (gi[i * H3 + 2 * H + c] - st[i][0]) * st[i][1];
+            const float h_r = (gh[i * H3 + c] - st[i][2]) * st[i][3];
+            const float h_z = (gh[i * H3 + H + c] - st[i][2]) * st[i][3];
+            const float h_n = (gh[i * H3 + 2 * H + c] - st[i][2]) * st[i][3];
+            const float rg = sigmoidf_(i_r + bir + h_r + bhr);
+            const float zg = sigmoidf_(i_z + biz + h_z + bhz);
+            const float ng = tanhf(i_n + bin + rg * (h_n + bhn));
+            const float hv = hrow[i * H + c];
+            hy[row * H + c] = ng + zg * (hv - ng);
+        }
+    }
+    __syncwarp();
+}
+
 template <int kRW>
 __global__ void __launch_bounds__(kGruWarps * 32)
 gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
@@ -154,60 +190,27 @@ gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H, kRW);
-    const float* hrow = scratch;
-    const float* gi = scratch + 3 * kRW * H;
-    const float* gh = gi + kRW * 3 * H;
-    const int H3 = 3 * H;
-    const bool has_bias = flags & SPG_GRU_BIAS;
     const int64_t warps_total = (int64_t)gridDim.x * kGruWarps;
     for (int64_t row0 = ((int64_t)blockIdx.x * kGruWarps + warp) * kRW; row0 < n_rows;
          row0 += warps_total * kRW) {
         float st[kRW][4];
         gru_rows_forward<kRW>(sm, scratch, H, flags, x, h, b_ig, row0, n_rows, lane, st);
-        for (int c = lane; c < H; c += 32) {
-            const float bir = has_bias ? b_ih[c] : 0.f, biz = has_bias ? b_ih[H + c] : 0.f,
-                        bin = has_bias ? b_ih[2 * H + c] : 0.f;
-            const float bhr = has_bias ? b_hh[c] : 0.f, bhz = has_bias ? b_hh[H + c] : 0.f,
-                        bhn = has_bias ? b_hh[2 * H + c] : 0.f;
-#pragma unroll
-            for (int i = 0; i < kRW; ++i) {
-                const int64_t row = row0 + i;
-                if (row >= n_rows) break;
-                const float i_r = (gi[i * H3 + c] - st[i][0]) * st[i][1];
-                const float i_z = (gi[i * H3 + H + c] - st[i][0]) * st[i][1];
-                const float i_n = (gi[i * H3 + 2 * H + c] - st[i][0]) * st[i][1];
-                const float h_r = (gh[i * H3 + c] - st[i][2]) * st[i][3];
-                const float h_z = (gh[i * H3 + H + c] - st[i][2]) * st[i][3];
-                const float h_n = (gh[i * H3 + 2 * H + c] - st[i][2]) * st[i][3];
-                const float rg = sigmoidf_(i_r + bir + h_r + bhr);
-                const float zg = sigmoidf_(i_z + biz + h_z + bhz);
-                const float ng = tanhf(i_n + bin + rg * (h_n + bhn));
-                const float hv = hrow[i * H + c];
-                hy[row * H + c] = ng + zg * (hv - ng);
-            }
-        }
-        __syncwarp();
+        gru_rows_emit<kRW>(scratch, H, flags, b_ih, b_hh, hy, row0, n_rows, lane, st);
     }
 }
 
+// Backward of the cell for the RW rows starting at row0 (one warp).  x, h and gy may have been
+// written earlier in the same kernel (fused recurrent kernels), hence no __restrict__ on them.
 template <int NU, int kRW>
-__global__ void __launch_bounds__(kGruWarps * 32)
-gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
-               const float* __restrict__ gy, const float* __restrict__ w_ih,
-               const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-               const float* __restrict__ b_hh, const float* __restrict__ w_ig,
-               const float* __restrict__ b_ig, float* __restrict__ d_x, float* __restrict__ d_h,
-               float* __restrict__ d_gi_out, float* __restrict__ d_gh_out,
-               float* __restrict__ d_q_out, float* __restrict__ xprime_out,
-               float* __restrict__ dpre_out, int64_t n_rows, int H, int flags) {
-    extern __shared__ float sm[];
-    gru_load_weights(sm, w_ih, w_hh, w_ig, H, flags & SPG_GRU_INGATE);
-    __syncthreads();
+__device__ __forceinline__ void gru_rows_backward(
+    const float* sm, float* scratch, int H, int flags, const float* x, const float* h,
+    const float* gy, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+    const float* __restrict__ b_ig, float* d_x, float* d_h, float* __restrict__ d_gi_out,
+    float* __restrict__ d_gh_out, float* __restrict__ d_q_out, float* __restrict__ xprime_out,
+    float* dpre_out, int64_t row0, int64_t n_rows, int lane) {
     const float* Wig_t = sm;
     const float* Wih_t = Wig_t + H * (H + 1);
     const float* Whh_t = Wih_t + H * (3 * H + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H, kRW);
     float* hrow = scratch;
     float* xrow = hrow + kRW * H;   // x' (gated input)
     float* srow = xrow + kRW * H;   // sigmoid(q); reused below for d_q
@@ -217,9 +220,7 @@ gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     const bool has_bias = flags & SPG_GRU_BIAS;
     const bool ln = flags & SPG_GRU_LAYERNORM;
     const bool ingate = flags & SPG_GRU_INGATE;
-    const int64_t warps_total = (int64_t)gridDim.x * kGruWarps;
-    for (int64_t row0 = ((int64_t)blockIdx.x * kGruWarps + warp) * kRW; row0 < n_rows;
-         row0 += warps_total * kRW) {
+    {
         float st[kRW][4];
         gru_rows_forward<kRW>(sm, scratch, H, flags, x, h, b_ig, row0, n_rows, lane, st);
         // ---- gate gradients (w.r.t. the normalised gate inputs), in place over gi/gh
@@ -386,6 +387,200 @@ gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
     }
 }
 
+template <int NU, int kRW>
+__global__ void __launch_bounds__(kGruWarps * 32)
+gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+               const float* __restrict__ gy, const float* __restrict__ w_ih,
+               const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+               const float* __restrict__ b_hh, const float* __restrict__ w_ig,
+               const float* __restrict__ b_ig, float* __restrict__ d_x, float* __restrict__ d_h,
+               float* __restrict__ d_gi_out, float* __restrict__ d_gh_out,
+               float* __restrict__ d_q_out, float* __restrict__ xprime_out,
+               float* __restrict__ dpre_out, int64_t n_rows, int H, int flags) {
+    extern __shared__ float sm[];
+    gru_load_weights(sm, w_ih, w_hh, w_ig, H, flags & SPG_GRU_INGATE);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* scratch = sm + gru_weight_floats(H) + warp * gru_scratch_floats(H, kRW);
+    const int64_t warps_total = (int64_t)gridDim.x * kGruWarps;
+    for (int64_t row0 = ((int64_t)blockIdx.x * kGruWarps + warp) * kRW; row0 < n_rows;
+         row0 += warps_total * kRW)
+        gru_rows_backward<NU, kRW>(sm, scratch, H, flags, x, h, gy, b_ih, b_hh, b_ig, d_x, d_h,
+                                   d_gi_out, d_gh_out, d_q_out, xprime_out, dpre_out, row0, n_rows,
+                                   lane);
+}
+
+
+// ------------------------------------------------------------------ fused recurrence
+// The R x {ECC, cell} loop of RNNGraphConvModule (ref: learning/modules.py:160-180) as ONE
+// persistent kernel each way, for the training-batch regime (a few thousand superpoints) where
+// 2R..3R separate launches are pure latency.  A warp owns a node for the whole recurrence:
+//   forward   r:  inp_i = ECC(h_r)_i  ->  h_{r+1,i} = cell(inp_i, h_{r,i})   | grid barrier
+//   backward  r:  (d_inp_i, d_h_i) = cell'(g_i)  | grid barrier |  g_i = d_h_i + ECC'(d_inp)_i (+cat)
+// so only the neighbour exchange crosses the barrier; the cell weights are loaded into shared
+// memory once per CTA instead of once per step.  Vector filters, H = 32, fp32, no idxe.
+constexpr int kRecH = 32;
+
+// All CTAs are co-resident (the launchers cap the grid with the occupancy API); `counter` counts
+// arrivals monotonically and is zeroed by the launcher.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+    return __ldcg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ float4 slot_reduce(float4 acc) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kGruWarps * 32)
+rnn_vv_fwd_kernel(float* hs, float* inps, const float4* __restrict__ w,
+                  const int* __restrict__ rowptr, const int* __restrict__ idxn,
+                  const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                  const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                  const float* __restrict__ w_ig, const float* __restrict__ b_ig, int n, int R,
+                  int flags, unsigned* barrier) {
+    extern __shared__ float sm[];
+    gru_load_weights(sm, w_ih, w_hh, w_ig, kRecH, flags & SPG_GRU_INGATE);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane >> 3, sub = lane & 7;
+    float* scratch = sm + gru_weight_floats(kRecH) + warp * gru_scratch_floats(kRecH, 1);
+    const int gwarp = blockIdx.x * kGruWarps + warp, nwarps = gridDim.x * kGruWarps;
+    for (int r = 0; r < R; ++r) {
+        float* hcur = hs + (size_t)r * n * kRecH;
+        float* hnext = hcur + (size_t)n * kRecH;
+        float* inp = inps + (size_t)r * n * kRecH;
+        for (int node = gwarp; node < n; node += nwarps) {
+            const int beg = rowptr[node], end = rowptr[node + 1];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int e = beg + slot;
+            for (; e + 4 < end; e += 8) {
+                const int s0 = __ldg(idxn + e), s1 = __ldg(idxn + e + 4);
+                const float4 w0 = __ldg(w + (int64_t)e * 8 + sub);
+                const float4 w1 = __ldg(w + (int64_t)(e + 4) * 8 + sub);
+                const float4 x0 = ldcg4(hcur + (int64_t)s0 * kRecH + sub * 4);
+                const float4 x1 = ldcg4(hcur + (int64_t)s1 * kRecH + sub * 4);
+                acc.x = fmaf(x0.x, w0.x, acc.x); acc.y = fmaf(x0.y, w0.y, acc.y);
+                acc.z = fmaf(x0.z, w0.z, acc.z); acc.w = fmaf(x0.w, w0.w, acc.w);
+                acc.x = fmaf(x1.x, w1.x, acc.x); acc.y = fmaf(x1.y, w1.y, acc.y);
+                acc.z = fmaf(x1.z, w1.z, acc.z); acc.w = fmaf(x1.w, w1.w, acc.w);
+            }
+            if (e < end) {
+                const int s0 = __ldg(idxn + e);
+                const float4 w0 = __ldg(w + (int64_t)e * 8 + sub);
+                const float4 x0 = ldcg4(hcur + (int64_t)s0 * kRecH + sub * 4);
+                acc.x = fmaf(x0.x, w0.x, acc.x); acc.y = fmaf(x0.y, w0.y, acc.y);
+                acc.z = fmaf(x0.z, w0.z, acc.z); acc.w = fmaf(x0.w, w0.w, acc.w);
+            }
+            acc = slot_reduce(acc);
+            if (slot == 0) {
+                const int deg = end - beg;
+                if (deg > 0) {
+                    const float d = (float)deg;
+                    acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
+                }
+                *reinterpret_cast<float4*>(inp + (int64_t)node * kRecH + sub * 4) = acc;
+            }
+            __syncwarp();
+            float st[1][4];
+            gru_rows_forward<1>(sm, scratch, kRecH, flags, inp, hcur, b_ig, node, n, lane, st);
+            gru_rows_emit<1>(scratch, kRecH, flags, b_ih, b_hh, hnext, node, n, lane, st);
+        }
+        if (r + 1 < R) grid_barrier(barrier, (unsigned)(r + 1) * gridDim.x);
+    }
+}
+
+__global__ void __launch_bounds__(kGruWarps * 32)
+rnn_vv_bwd_kernel(const float* __restrict__ hs, const float* __restrict__ inps,
+                  const float4* __restrict__ w, const float* __restrict__ gtop,
+                  const float* __restrict__ gcat, const int* __restrict__ tgt_rowptr,
+                  const int* __restrict__ src_rowptr, const int* __restrict__ src_perm,
+                  const int* __restrict__ edge_tgt, const float* __restrict__ w_ih,
+                  const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                  const float* __restrict__ b_hh, const float* __restrict__ w_ig,
+                  const float* __restrict__ b_ig, float* ginp, float* dh, float* gh,
+                  float* __restrict__ d_gi, float* __restrict__ d_gh, float* __restrict__ d_q,
+                  float* __restrict__ xp, float* dpre, int n, int R, int flags,
+                  unsigned* barrier) {
+    extern __shared__ float sm[];
+    gru_load_weights(sm, w_ih, w_hh, w_ig, kRecH, flags & SPG_GRU_INGATE);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane >> 3, sub = lane & 7;
+    float* scratch = sm + gru_weight_floats(kRecH) + warp * gru_scratch_floats(kRecH, 1);
+    const int gwarp = blockIdx.x * kGruWarps + warp, nwarps = gridDim.x * kGruWarps;
+    const size_t plane = (size_t)n * kRecH;
+    for (int r = R - 1; r >= 0; --r) {
+        const float* gy = (r == R - 1) ? gtop : gh;   // gh rows are produced by the same warp
+        float* ginp_r = ginp + r * plane;
+        for (int node = gwarp; node < n; node += nwarps)
+            gru_rows_backward<1, 1>(sm, scratch, kRecH, flags, inps + r * plane, hs + r * plane, gy,
+                                    b_ih, b_hh, b_ig, ginp_r, dh, d_gi + 3 * r * plane,
+                                    d_gh + 3 * r * plane, d_q + r * plane, xp + r * plane,
+                                    dpre + 4 * r * plane, node, n, lane);
+        grid_barrier(barrier, (unsigned)(R - r) * gridDim.x);
+        for (int node = gwarp; node < n; node += nwarps) {
+            const int beg = src_rowptr[node], end = src_rowptr[node + 1];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = beg + slot; p < end; p += 4) {
+                const int e = __ldg(src_perm + p);
+                const int tg = __ldg(edge_tgt + e);
+                const float4 wv = __ldg(w + (int64_t)e * 8 + sub);
+                const float inv = 1.f / (float)(__ldg(tgt_rowptr + tg + 1) - __ldg(tgt_rowptr + tg));
+                const float4 gv = ldcg4(ginp_r + (int64_t)tg * kRecH + sub * 4);
+                acc.x = fmaf(wv.x, gv.x * inv, acc.x); acc.y = fmaf(wv.y, gv.y * inv, acc.y);
+                acc.z = fmaf(wv.z, gv.z * inv, acc.z); acc.w = fmaf(wv.w, gv.w * inv, acc.w);
+            }
+            acc = slot_reduce(acc);
+            if (slot == 0) {
+                const float4 a = *reinterpret_cast<const float4*>(dh + (int64_t)node * kRecH + sub * 4);
+                acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                if (gcat) {
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(
+                        gcat + r * plane + (int64_t)node * kRecH + sub * 4));
+                    acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+                }
+                *reinterpret_cast<float4*>(gh + (int64_t)node * kRecH + sub * 4) = acc;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static inline int rnn_grid(const void* kernel, size_t smem, int n) {
+    int per_sm = 0, sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGruWarps * 32, smem) !=
+        cudaSuccess)
+        return -1;
+    if (per_sm > 2) per_sm = 2;
+    int64_t blocks = ceil_div64(n, kGruWarps);
+    const int64_t cap = (int64_t)per_sm * sms;
+    if (blocks > cap) blocks = cap;
+    return (int)blocks;   // 0 if the kernel does not fit at all
+}
+
 static inline size_t gru_smem_bytes(int H, int rw) {
     return sizeof(float) * ((size_t)gru_weight_floats(H) + (size_t)kGruWarps * gru_scratch_floats(H, rw));
 }
@@ -465,6 +660,70 @@ int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const floa
     else SPG_GRU_BWD_CASE(4)
 #undef SPG_GRU_BWD_CASE
 #undef SPG_GRU_BWD_CASE2
+    return launch_status();
+}
+
+int spg_rnn_vv_supported(int64_t n_nodes, int hidden) {
+    return hidden == kRecH && n_nodes > 0 && gru_rows_per_warp(n_nodes) == 1;
+}
+
+int spg_rnn_vv_fwd(float* hs, float* inps, const float* w, const int32_t* tgt_rowptr,
+                   const int32_t* idxn, const float* weight_ih, const float* weight_hh,
+                   const float* bias_ih, const float* bias_hh, const float* ig_weight,
+                   const float* ig_bias, int64_t n_nodes, int hidden, int n_repeats, int flags,
+                   void* barrier_ws, spg_stream_t stream) {
+    if (n_nodes < 0 || n_repeats < 0) return SPG_E_BADARG;
+    if (n_nodes == 0 || n_repeats == 0) return SPG_OK;
+    if (!spg_rnn_vv_supported(n_nodes, hidden)) return SPG_E_UNSUPPORTED;
+    if (!hs || !inps || !w || !tgt_rowptr || !idxn || !weight_ih || !weight_hh || !barrier_ws)
+        return SPG_E_BADARG;
+    if ((flags & SPG_GRU_BIAS) && (!bias_ih || !bias_hh)) return SPG_E_BADARG;
+    if ((flags & SPG_GRU_INGATE) && (!ig_weight || !ig_bias)) return SPG_E_BADARG;
+    const size_t smem = gru_smem_bytes(hidden, 1);
+    cudaError_t e = cudaFuncSetAttribute(rnn_vv_fwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int blocks = rnn_grid((const void*)rnn_vv_fwd_kernel, smem, (int)n_nodes);
+    if (blocks <= 0) return SPG_E_UNSUPPORTED;
+    e = cudaMemsetAsync(barrier_ws, 0, sizeof(unsigned), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    SPG_LAUNCH(K_RNN_FWD, (cudaStream_t)stream, rnn_vv_fwd_kernel, (unsigned)blocks,
+               kGruWarps * 32, smem, hs, inps, reinterpret_cast<const float4*>(w), tgt_rowptr, idxn,
+               weight_ih, weight_hh, bias_ih, bias_hh, ig_weight, ig_bias, (int)n_nodes, n_repeats,
+               flags, reinterpret_cast<unsigned*>(barrier_ws));
+    return launch_status();
+}
+
+int spg_rnn_vv_bwd(const float* hs, const float* inps, const float* w, const float* grad_top,
+                   const float* grad_cat, const int32_t* tgt_rowptr, const int32_t* src_rowptr,
+                   const int32_t* src_perm, const int32_t* edge_tgt, const float* weight_ih,
+                   const float* weight_hh, const float* bias_ih, const float* bias_hh,
+                   const float* ig_weight, const float* ig_bias, float* grad_inp, float* d_h_ws,
+                   float* grad_h0, float* d_gi, float* d_gh, float* d_q, float* xprime,
+                   float* dpre, int64_t n_nodes, int hidden, int n_repeats, int flags,
+                   void* barrier_ws, spg_stream_t stream) {
+    if (n_nodes < 0 || n_repeats < 0) return SPG_E_BADARG;
+    if (n_nodes == 0 || n_repeats == 0) return SPG_OK;
+    if (!spg_rnn_vv_supported(n_nodes, hidden)) return SPG_E_UNSUPPORTED;
+    if (!hs || !inps || !w || !grad_top || !tgt_rowptr || !src_rowptr || !src_perm || !edge_tgt ||
+        !weight_ih || !weight_hh || !grad_inp || !d_h_ws || !grad_h0 || !d_gi || !d_gh || !d_q ||
+        !xprime || !dpre || !barrier_ws)
+        return SPG_E_BADARG;
+    if ((flags & SPG_GRU_BIAS) && (!bias_ih || !bias_hh)) return SPG_E_BADARG;
+    if ((flags & SPG_GRU_INGATE) && (!ig_weight || !ig_bias)) return SPG_E_BADARG;
+    const size_t smem = gru_smem_bytes(hidden, 1);
+    cudaError_t e = cudaFuncSetAttribute(rnn_vv_bwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int blocks = rnn_grid((const void*)rnn_vv_bwd_kernel, smem, (int)n_nodes);
+    if (blocks <= 0) return SPG_E_UNSUPPORTED;
+    e = cudaMemsetAsync(barrier_ws, 0, sizeof(unsigned), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    SPG_LAUNCH(K_RNN_BWD, (cudaStream_t)stream, rnn_vv_bwd_kernel, (unsigned)blocks,
+               kGruWarps * 32, smem, hs, inps, reinterpret_cast<const float4*>(w), grad_top,
+               grad_cat, tgt_rowptr, src_rowptr, src_perm, edge_tgt, weight_ih, weight_hh, bias_ih,
+               bias_hh, ig_weight, ig_bias, grad_inp, d_h_ws, grad_h0, d_gi, d_gh, d_q, xprime,
+               dpre, (int)n_nodes, n_repeats, flags, reinterpret_cast<unsigned*>(barrier_ws));
     return launch_status();
 }
 

@@ -16,7 +16,7 @@ static const char* kKernelNames[K_COUNT] = {
     "act_bwd_reduce_final", "act_bwd_apply",   "cloud_rows",          "segmax_fwd",
     "segmax_bwd",        "stn_apply_bwd",      "rows_scatter",        "rows_gather",
     "ce_loss",           "ce_loss_final",      "clamp_adam",          "tc_gemm_3xtf32",
-    "tc_pack_weights",     "tc_dw_3xtf32",
+    "tc_pack_weights",     "tc_dw_3xtf32",       "rnn_ecc_gru_fwd",     "rnn_ecc_gru_bwd",
 };
 
 struct Record {

@@ -196,6 +196,42 @@ def gru_bwd(x, h, gy, w_ih, w_hh, b_ih, b_hh, w_ig, b_ig, flags, d_gi, d_gh, d_q
     return d_x, d_h
 
 
+def rnn_vv_supported(weights, graph, n, H):
+    """True when the fused recurrence kernels apply (vector filters, H == 32, no idxe, training-batch
+    sizes); everything else runs the per-step kernels."""
+    return (USE_FUSED_RNN[0] and weights.dim() == 2 and weights.dtype == torch.float32
+            and graph.idxe_host is None and graph.n_in == n and graph.n_out == n
+            and bool(_lib.lib().spg_rnn_vv_supported(n, H)))
+
+
+def rnn_vv_fwd(hs, inps, weights, graph, cell, flags):
+    """hs [R+1,n,H] with hs[0] set, inps [R,n,H]; fills hs[1:], inps (ref: learning/modules.py:160-180)."""
+    _need_cuda(hs, inps, weights)
+    R, n, H = inps.shape
+    g = graph.to(hs.device)
+    w_ih, w_hh, b_ih, b_hh, w_ig, b_ig = cell
+    bar = torch.empty(4, dtype=torch.int32, device=hs.device)
+    _lib.call("spg_rnn_vv_fwd", hs, inps, _c(weights), g["tgt_rowptr"], g["idxn"], _c(w_ih), _c(w_hh),
+              b_ih, b_hh, None if w_ig is None else _c(w_ig), b_ig, n, H, R, flags, bar,
+              _lib.current_stream())
+
+
+def rnn_vv_bwd(hs, inps, weights, graph, cell, flags, gtop, gcat, ginp, d_gi, d_gh, d_q, xp, dpre):
+    """Backward of rnn_vv_fwd; returns the gradient w.r.t. hs[0]."""
+    _need_cuda(hs, inps, weights, gtop)
+    R, n, H = inps.shape
+    g = graph.to(hs.device)
+    w_ih, w_hh, b_ih, b_hh, w_ig, b_ig = cell
+    bar = torch.empty(4, dtype=torch.int32, device=hs.device)
+    dh = torch.empty((n, H), dtype=torch.float32, device=hs.device)
+    gh0 = torch.empty((n, H), dtype=torch.float32, device=hs.device)
+    _lib.call("spg_rnn_vv_bwd", hs, inps, _c(weights), gtop, gcat, g["tgt_rowptr"], g["src_rowptr"],
+              g["src_perm"], g["edge_tgt"], _c(w_ih), _c(w_hh), b_ih, b_hh,
+              None if w_ig is None else _c(w_ig), b_ig, ginp, dh, gh0, d_gi, d_gh, d_q, xp, dpre,
+              n, H, R, flags, bar, _lib.current_stream())
+    return gh0
+
+
 # ---------------------------------------------------------------------------- dense
 GEMM_TRACE = None  # set to [] to record (description, start, end) events of every SIMT gemm call
 GEMM_FLOPS = [0]  # algorithmic FLOPs (2*M*N*K) issued through gemm(); read by bench.py
@@ -259,6 +295,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
 
 
 USE_TC = [os.environ.get("SPG_TC", "1") != "0"]  # tcgen05 path for the large point-wise layers
+USE_FUSED_RNN = [os.environ.get("SPG_FUSED_RNN", "1") != "0"]  # one-kernel R x {ECC, cell} loop
 
 
 def tc_supported(M, N, K, lda=0, ldc=0):

@@ -184,10 +184,15 @@ class _RecurrentECCFunction(torch.autograd.Function):
         w = _unpack_cell(flags, cpresent)
         hs = torch.empty((nrepeats + 1, N, H), dtype=torch.float32, device=dev)
         hs[0].copy_(hx)
-        inps = torch.empty((nrepeats, N, H), dtype=torch.float32, device=dev) if training else None
-        for r in range(nrepeats):
-            inp = ops.ecc_fwd(hs[r], weights, graph, H, out=inps[r] if training else None)
-            ops.gru_fwd(inp, hs[r], *w, flags, out=hs[r + 1])
+        fused = nrepeats > 0 and ops.rnn_vv_supported(weights, graph, N, H)
+        inps = (torch.empty((nrepeats, N, H), dtype=torch.float32, device=dev)
+                if training or fused else None)
+        if fused:
+            ops.rnn_vv_fwd(hs, inps, weights, graph, w, flags)
+        else:
+            for r in range(nrepeats):
+                inp = ops.ecc_fwd(hs[r], weights, graph, H, out=inps[r] if training else None)
+                ops.gru_fwd(inp, hs[r], *w, flags, out=hs[r + 1])
         if training:
             ctx.save_for_backward(hs, inps, weights)
         ctx.meta = (graph, fspecs, n_fparams, flags, nrepeats, cat_all, training, fsaved,
@@ -219,13 +224,17 @@ class _RecurrentECCFunction(torch.autograd.Function):
         xp = torch.empty((R, N, H), device=dev)
         dpre = torch.empty((R, N, 4 * H), device=dev)
         ginp = torch.empty((R, N, H), device=dev)
-        for r in range(R - 1, -1, -1):
-            d_x, d_h = ops.gru_bwd(inps[r], hs[r], gh, *w, flags, d_gi[r], d_gh[r], d_q[r], xp[r],
-                                   dpre[r], d_x=ginp[r])
-            # gradient w.r.t. h_r: through the cell (d_h), through the ECC (source-CSR gather) and,
-            # with cat_all, the direct gradient of the concatenated output
-            gh = ops.ecc_bwd_x(weights, d_x, graph, H, add0=d_h,
-                               add1=None if gcat is None else gcat[r])
+        if R > 0 and ops.rnn_vv_supported(weights, graph, N, H):
+            gh = ops.rnn_vv_bwd(hs, inps, weights, graph, w, flags, gh, gcat, ginp, d_gi, d_gh, d_q,
+                                xp, dpre)
+        else:
+            for r in range(R - 1, -1, -1):
+                d_x, d_h = ops.gru_bwd(inps[r], hs[r], gh, *w, flags, d_gi[r], d_gh[r], d_q[r],
+                                       xp[r], dpre[r], d_x=ginp[r])
+                # gradient w.r.t. h_r: through the cell (d_h), through the ECC (source-CSR gather)
+                # and, with cat_all, the direct gradient of the concatenated output
+                gh = ops.ecc_bwd_x(weights, d_x, graph, H, add0=d_h,
+                                   add1=None if gcat is None else gcat[r])
         # filter gradient of all R steps in one pass
         g_w = ops.ecc_bwd_w(hs[:R], ginp, graph, tuple(weights.shape), n_iter=R)
         grads_f = [None] * n_fparams

@@ -398,9 +398,12 @@ MCFG = {
 }
 
 
-@pytest.mark.parametrize("tag", ["vv", "cat", "mat"])
-def test_graphnet_golden(golden_dir, dev, tag):
+@pytest.mark.parametrize("tag,fused", [("vv", True), ("vv", False), ("cat", True), ("cat", False),
+                                       ("mat", False)])
+def test_graphnet_golden(golden_dir, dev, tag, fused, monkeypatch):
+    from superpoint_graph_b200 import ops
     from superpoint_graph_b200.spg_ecc import GraphConvInfo
+    monkeypatch.setattr(ops, "USE_FUSED_RNN", [fused])
     from superpoint_graph_b200.spg_graphnet import GraphNetwork
     g = load(golden_dir, "graphnet_%s.npz" % tag)
     net = GraphNetwork(str(g["config"]), 32, [13, 32, 128, 64], True, 0, 2, 1e20, use_pyg=0, cuda=True)
@@ -611,3 +614,33 @@ def test_graph_conv_module_matrix_filters(dev):
     close(out, ref)
     out.backward(gout.to(dev))
     close_grads({k: p.grad for k, p in fnet.named_parameters()}, {k: v.grad for k, v in sd.items()}, 3e-4)
+
+
+@pytest.mark.parametrize("n_nodes,cat_all", [(1024, False), (1024, True), (5000, True), (37, False)])
+def test_fused_recurrence_is_bit_identical_to_per_step_kernels(dev, monkeypatch, n_nodes, cat_all):
+    """One-kernel R x {ECC, cell} loop (grid barrier between steps) vs. the 2R / 3R separate
+    launches: same device functions, same summation order -> identical bits, forward and backward."""
+    from superpoint_graph_b200 import ops, synthetic
+    from superpoint_graph_b200.spg_ecc import GraphConvInfo
+    from superpoint_graph_b200.spg_graphnet import create_fnet
+    from superpoint_graph_b200.spg_modules import RNNGraphConvModule, GRUCellEx
+    torch.manual_seed(3)
+    b = synthetic.make_batch(n_nodes, k=8, seed=11, npts=8, minpts=4)
+    gi = GraphConvInfo.from_arrays(b["idxn"].numpy(), b["degs"].numpy(), b["edgefeats"].numpy())
+    gi.cuda()
+    fnet = create_fnet([13, 32, 128, 64, 32], True, 0, 2)
+    mod = RNNGraphConvModule(GRUCellEx(32, 32, bias=True, layernorm=True, ingate=True), fnet, 32,
+                             vv=True, gc_info=gi, nrepeats=10, cat_all=cat_all, use_pyg=False,
+                             cuda=True).to(dev).train()
+    x0 = torch.randn(n_nodes, 32, device=dev)
+    results = []
+    for fused in (True, False):
+        monkeypatch.setattr(ops, "USE_FUSED_RNN", [fused])
+        assert ops.rnn_vv_supported(torch.empty(1, 32, device=dev), gi.graph(), n_nodes, 32) == fused
+        mod.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        y = mod(x)
+        (y * torch.linspace(-1, 1, y.numel(), device=dev).view_as(y)).sum().backward()
+        results.append([y.detach(), x.grad] + [p.grad.clone() for p in mod.parameters()])
+    for a, c in zip(*results):
+        assert torch.equal(a, c)
