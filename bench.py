@@ -242,6 +242,17 @@ def cpu_baseline(batch, counts, margs, sd_ptn, sd_ecc, budget_s=25.0):
             "vectorized_ms_per_step": out["vec"][0] * 1e3}
 
 
+def ncu_traffic():
+    """Per-launch DRAM traffic of the dominant kernels from the committed ncu captures
+    (profiles/ncu_traffic.json); {} if the file is missing."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def ecc_roofline(dev, n_nodes, pk):
     """ECC gather-product-scatter kernels at sweep size (configs[4]: 100k superpoints, ~1M edges;
     filter banks far larger than L2).  Algorithmic bytes per SURVEY.md §8(d)."""
@@ -476,6 +487,12 @@ def run_b200(args):
                     dense[name] = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
                                    "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
                                    "share_of_step": ks[name][1] / tot, "note": notes[name]}
+            for name, obj in dense.items():
+                tr = ncu_traffic().get(name)
+                if tr:
+                    obj["traffic"] = tr["bytes_per_launch"]
+                    obj["traffic_note"] = "ncu --set full, %s (%s); algorithmic %.4g B" % (
+                        tr["launch"], tr["source"], tr["algorithmic_bytes"])
             gname = top[0][0]
             if gname in dense:
                 line["roofline"] = dense[gname]
@@ -487,6 +504,11 @@ def run_b200(args):
             ecc_obj = {"kernel": "ecc_mat_fwd", "bound": "hbm", "achieved": k["gbs"], "peak": pk["hbm"],
                        "unit": "GB/s", "frac": k["frac"], "traffic": None,
                        "workload": "configs[4]-scale: %d superpoints, %d edges, [E,32,32] filters" % (er["nodes"], er["edges"])}
+            tr = ncu_traffic().get("ecc_mat_fwd")
+            if tr and tr.get("nodes") == er["nodes"]:
+                ecc_obj["traffic"] = tr["bytes_per_launch"]
+                ecc_obj["traffic_note"] = "ncu --set full, %s (%s); algorithmic %.4g B" % (
+                    tr["launch"], tr["source"], tr["algorithmic_bytes"])
             if "roofline" not in line:
                 line["roofline"] = ecc_obj
             else:

@@ -95,6 +95,41 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // Producer threads put their first A chunks in flight before anything else: the global-load
+    // latency then overlaps the resident-weight load and the CTA-wide barrier below.
+    // Register-level prefetch ring: PF chunks of A are in flight per thread (the global-load
+    // latency, ~2 us under load, is far longer than one chunk's transform + MMA).
+    constexpr int PF = 4;
+    float4 q[PF][4];
+    const int pt = t - (T2_EPI_WARPS + 1) * 32;  // producer thread id 0..255 (negative: other roles)
+    auto load = [&](int64_t tile, int kc, float4 (&dst)[4]) {
+        const int64_t m0 = tile * T2_BM;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = pt + 256 * j;
+            const int row = i >> 3, c16 = i & 7;
+            dst[j] = (!(p.dbg & 4) && tile < tiles && m0 + row < p.M)
+                         ? __ldg(reinterpret_cast<const float4*>(p.A + (m0 + row) * p.lda +
+                                                                 kc * T2_KC + c16 * 4))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto advance = [&](int64_t& tl, int& k) {
+        if (++k == nk) {
+            k = 0;
+            tl += gridDim.x;
+        }
+    };
+    // load cursor (runs PF-1 items ahead of the consume cursor)
+    int64_t ltile = blockIdx.x;
+    int lkc = 0;
+    if (pt >= 0) {
+#pragma unroll
+        for (int d = 0; d < PF - 1; ++d) {
+            load(ltile, lkc, q[d]);
+            advance(ltile, lkc);
+        }
+    }
     // resident weight slice: rows [n0, n0+NS) of every (chunk, hi|lo) block of the image
     {
         const int f4_per_block = NS * T2_KC / 4;  // float4 per (chunk, half) block of the slice
@@ -126,38 +161,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
 
     if (warp >= T2_EPI_WARPS + 1) {
         // ================================ producers ================================
-        const int pt = t - (T2_EPI_WARPS + 1) * 32;  // 0..255
         const bool pro = p.a_scale || p.a_shift || p.a_relu;
-        // Register-level prefetch ring: PF chunks of A are in flight per thread (the global-load
-        // latency, ~2 us under load, is far longer than one chunk's transform + MMA).
-        constexpr int PF = 4;
-        float4 q[PF][4];
-        auto load = [&](int64_t tile, int kc, float4 (&dst)[4]) {
-            const int64_t m0 = tile * T2_BM;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = pt + 256 * j;
-                const int row = i >> 3, c16 = i & 7;
-                dst[j] = (!(p.dbg & 4) && tile < tiles && m0 + row < p.M)
-                             ? __ldg(reinterpret_cast<const float4*>(p.A + (m0 + row) * p.lda +
-                                                                     kc * T2_KC + c16 * 4))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        // load cursor (runs PF-1 items ahead of the consume cursor)
-        int64_t ltile = blockIdx.x;
-        int lkc = 0;
-        auto advance = [&](int64_t& tl, int& k) {
-            if (++k == nk) {
-                k = 0;
-                tl += gridDim.x;
-            }
-        };
-#pragma unroll
-        for (int d = 0; d < PF - 1; ++d) {
-            load(ltile, lkc, q[d]);
-            advance(ltile, lkc);
-        }
         int64_t tile = blockIdx.x;
         int kc = 0;
         uint32_t it = 0;
@@ -270,8 +274,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_gemm2_kernel(const Tc2Args p
             mbar_wait(bar_accfull(a), (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row0 = tile * T2_BM + w * 32;
-            const int64_t row = row0 + lane;
-            const bool valid = row < p.M;
             const float nvalid = (float)max((int64_t)0, min((int64_t)32, p.M - row0));
 #pragma unroll 1
             for (int cb = cb0; cb < NS / 32; cb += T2_EPI_WARPS / 4) {

@@ -305,6 +305,7 @@ def tc_supported(M, N, K, lda=0, ldc=0):
 
 PACK_CACHE = {}   # (W ptr, ldw, transpose, N, K, k_valid) -> image, valid until the weights change
 _PACK_TABLES = {}  # tuple of job keys -> (device table, images, total)
+PACK_LEARN = [None]  # dict owned by a Trainer: images packed on demand in its step, batched from the next step on
 
 
 def prepack(jobs):
@@ -343,6 +344,9 @@ def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=Fal
         img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
         _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, kv, img,
                   _lib.current_stream())
+        if PACK_LEARN[0] is not None:
+            PACK_LEARN[0][(W.data_ptr(), int(ldw), int(bool(transpose)), int(N), int(K), kv)] = (
+                W, int(ldw), bool(transpose), int(N), int(K), kv)
     out = torch.empty((M, N), dtype=torch.float32, device=dev)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
     tiles = int(_lib.lib().spg_tc_gemm_stats_partials(int(M), int(N), int(K)))

@@ -210,9 +210,11 @@ class PointNet(nn.Module):
                                        training, *params)
 
 
-def prepack_weights(ptn, n_clouds, n_points):
+def prepack_weights(ptn, n_clouds, n_points, extra=()):
     """One launch that builds every tensor-core weight image the next training forward+backward of
-    `ptn` on [n_clouds, F, n_points] will use (called by the Trainer at the start of a step)."""
+    `ptn` on [n_clouds, F, n_points] will use (called by the Trainer at the start of a step).
+    `extra`: further (W, ldw, transpose, N, K, k_valid) jobs, e.g. the ones a previous step had to
+    pack on demand (small FC layers, filter net, classifier)."""
     from .dense import pack_jobs
 
     M = n_clouds * n_points
@@ -221,6 +223,8 @@ def prepack_weights(ptn, n_clouds, n_points):
     jobs = pack_jobs(conv_g, params, M, ld, ptn.nfeat_stn > 0)
     if stn_g is not None:
         jobs += pack_jobs(stn_g[0], params, M, ld, False)
+    seen = set((j[0].data_ptr(),) + tuple(int(v) for v in j[1:]) for j in jobs)
+    jobs += [j for j in extra if ((j[0].data_ptr(),) + tuple(int(v) for v in j[1:])) not in seen]
     ops.prepack(jobs)
 
 

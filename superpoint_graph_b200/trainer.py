@@ -125,6 +125,7 @@ class Trainer(object):
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
+        self._learned_packs = {}  # weight images packed on demand by earlier steps (see compute_gradients)
         self.step_dev = torch.zeros((), dtype=torch.int64, device=self.flat.device)
         self._graphs = {}
         self.class_weights = class_weights
@@ -145,14 +146,24 @@ class Trainer(object):
         self.model.train()
         for p in self.params:
             p.grad = None
-        prepack_weights(self.model.ptn, db.clouds.shape[0], db.clouds.shape[2])
-        logits = self.forward(db)
-        loss, d_logits = ops.ce_loss(logits, db.labels, self.class_weights, -100)
-        logits.backward(d_logits)
+        # weight images: the point-wise layers are known in advance, the rest (FC layers, filter net,
+        # classifier) is learned from the on-demand packs of the previous step -> one launch
+        self._prepack(db)
+        ops.PACK_LEARN[0] = self._learned_packs
+        try:
+            logits = self.forward(db)
+            loss, d_logits = ops.ce_loss(logits, db.labels, self.class_weights, -100)
+            logits.backward(d_logits)
+        finally:
+            ops.PACK_LEARN[0] = None
         self.embedder.bw_hook()
         ops.PACK_CACHE.clear()  # the optimizer is about to change the weights
         torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_grad)
         return loss, logits.detach()
+
+    def _prepack(self, db):
+        prepack_weights(self.model.ptn, db.clouds.shape[0], db.clouds.shape[2],
+                        extra=list(self._learned_packs.values()))
 
     def apply_update(self):
         """One all-reduce of the flat gradient (scene-parallel ranks), then clamp + Adam in one
@@ -180,6 +191,10 @@ class Trainer(object):
         key = key if key is not None else id(db)
         for _ in range(warmup):
             self.train_step(db)
+        # the job table of the batched weight packing is uploaded on first use: do that outside
+        # the capture (a pageable H2D copy cannot be captured)
+        self._prepack(db)
+        ops.PACK_CACHE.clear()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
