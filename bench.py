@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "spg_train_step_edges_plus_points_per_sec"
@@ -289,6 +290,61 @@ def ecc_roofline(dev, n_nodes, pk):
     return dict(nodes=N, edges=E, kernels=res)
 
 
+def loader_roofline(dev, pk, with_cpu):
+    """Per-superpoint batch loader: `spg_cloud_build` on 32768 resident
+    superpoints of 40..600 points (S3DIS attributes, L=128) against the HBM roofline, and the
+    reference's numpy `load_superpoint` (oracle port) on a bounded sample of the same superpoints.
+    Algorithmic bytes per output point: F*4 read + 4 (sample index) + F*4 written."""
+    from types import SimpleNamespace
+
+    from superpoint_graph_b200 import ops
+    from superpoint_graph_b200.spg_loader import attrib_columns
+    rng = np.random.default_rng(2)
+    nv, L, C = 32768, 128, 15
+    counts = rng.integers(40, 601, size=nv)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    host_pts = rng.standard_normal((int(counts.sum()), C), dtype=np.float32)
+    pts = torch.from_numpy(host_pts).to(dev)
+    idx = (rng.random((nv, L)) * counts[:, None]).astype(np.int32)
+    cols = attrib_columns("xyzrgbelpsvXYZ", C)
+    F = len(cols)
+    t_idx = torch.from_numpy(idx).to(dev)
+    t_start = torch.from_numpy(starts.astype(np.int64)).to(dev)
+    t_count = torch.from_numpy(counts.astype(np.int32)).to(dev)
+    t_cols = torch.tensor(cols, dtype=torch.int32, device=dev)
+    clouds = torch.empty((nv, F, L), dtype=torch.float32, device=dev)
+    diam = torch.empty(nv, dtype=torch.float32, device=dev)
+
+    def fn():
+        ops.cloud_build(pts, t_start, t_count, t_idx, t_cols, L, True, None, None, 0.0, 0.05, 0, clouds, diam)
+
+    for _ in range(3):
+        fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for s_, e_ in ev:
+        s_.record()
+        fn()
+        e_.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
+    nbytes = nv * L * (2 * F * 4 + 4)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out = {"kernel": "cloud_build", "bound": "hbm", "superpoints": nv, "points_resident": int(counts.sum()),
+           "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+           "frac": gbs / pk["hbm"], "traffic": None, "gpu_superpoints_per_s": nv / (ms * 1e-3)}
+    if with_cpu:
+        from oracle import loader_ref  # CPU baseline leg only
+        n_cpu = 2000
+        t0 = time.perf_counter()
+        for i in range(n_cpu):
+            P = host_pts[starts[i]:starts[i] + counts[i]]
+            loader_ref.load_superpoint(P, idx[i], "xyzrgbelpsvXYZ", 1)
+        dt = time.perf_counter() - t0
+        out["cpu_superpoints_per_s"] = n_cpu / dt
+        out["cpu_sample"] = "%d of the same superpoints, oracle port of load_superpoint, 1 thread (numpy)" % n_cpu
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -515,6 +571,10 @@ def run_b200(args):
                 line["roofline_ecc_scatter"] = ecc_obj
         except Exception as ex:  # keep the bench line even if the microbench cannot run
             line["roofline_ecc_error"] = repr(ex)
+        try:
+            line["roofline_loader"] = loader_roofline(dev, pk, not args.no_cpu_baseline)
+        except Exception as ex:
+            line["roofline_loader_error"] = repr(ex)
 
     if rank == 0 and world == 1 and args.trace_gemm:
         ops.GEMM_TRACE = []

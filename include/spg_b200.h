@@ -307,6 +307,37 @@ int spg_clamp_adam_dev(float* param, const float* grad, float* exp_avg, float* e
                        float grad_clip, float grad_scale, int64_t* step_counter,
                        spg_stream_t stream);
 
+/* ------------------------------------------- either side of the path  */
+/* Batch loader, per-superpoint part (ref: learning/spg.py:198-236 load_superpoint,
+ * :238-260 augment_cloud, stacked as cloud.T by loader :146-166).  The parsed points of
+ * the resident superpoints are one packed array points[rows, ldp] (columns as the
+ * reference's parsed files: xyz 0-2, rgb 3-5, e 6, lpsv 7-10, XYZ 11-13, d 14).
+ * For cloud i of n_clouds:
+ *   rows   = points[sp_start[i] + sample_idx[i, j]], j < n_points   (sample_idx NULL: the
+ *            first min(count, L) points as they are, the rest drawn on the device)
+ *   xyz    = xyz - mean(xyz) (sequential fp32 column sums, as numpy); if normalize:
+ *            diameter = max_k (max xyz_k - min xyz_k); xyz /= fp32(diameter + 1e-10)
+ *   out[f] = column columns[f] (columns < 3: the centred xyz)
+ *   out[0..2] = out[0..2] . xform[i]^T (double, rounded once) if xform != NULL
+ *   out   += jitter[i, j, f]  if jitter != NULL; else clip(jitter_sigma*N(0,1), +-jitter_clip)
+ *            from a counter-based generator keyed by `seed` if jitter_sigma > 0
+ *   clouds[i, f, j] = out[j, f];  diameters[i] = diameter (0 if !normalize)
+ * With host-provided sample_idx (and jitter) the result is bit-identical to the reference.  */
+int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
+                    const int32_t* sp_count, const int32_t* sample_idx, const int32_t* columns,
+                    int n_attribs, int n_points, int normalize, const double* xform,
+                    const float* jitter, float jitter_sigma, float jitter_clip, int64_t seed,
+                    float* clouds, float* diameters, int64_t n_clouds, spg_stream_t stream);
+/* Evaluation bookkeeping (ref: learning/main.py:257-262,297-305 + metrics.py:16-18):
+ * pred_i = first argmax of logits[i,:]; for nodes with label_mode[i] != -100:
+ * confusion[:, pred_i] += label_vec[i,:], counters[0] += 1, counters[1] += (pred_i == label_mode[i]).
+ * confusion [C,C] and counters [2] are int64 device arrays accumulated across calls (caller zeroes
+ * them); pred_out [n] (may be NULL) receives every node's prediction.                        */
+int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* label_mode,
+                        const int64_t* label_vec, int64_t ld_vec, int64_t* confusion,
+                        int64_t* counters, int64_t* pred_out, int64_t n_nodes, int n_classes,
+                        spg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

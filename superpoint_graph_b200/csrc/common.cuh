@@ -45,6 +45,8 @@ enum KernelId {
     K_TC_DW,
     K_RNN_FWD,
     K_RNN_BWD,
+    K_CLOUD_BUILD,
+    K_CONFUSION,
     K_COUNT
 };
 

@@ -1,0 +1,250 @@
+// The two steps either side of the training/inference path:
+//
+//  * cloud_build: the per-superpoint part of the reference's batch loader
+//    (learning/spg.py:198-236 `load_superpoint`, :238-260 `augment_cloud`, stacked by
+//    `loader` :146-166): resample every chosen superpoint to exactly L points, centre and scale
+//    xyz, select the attribute columns, augment, and emit the [Nv, F, L] tensor PointNet reads.
+//    The reference does this in numpy per superpoint from per-superpoint HDF5 datasets; here the
+//    parsed points stay resident in HBM as one packed [rows, ldp] array and a CTA builds one cloud.
+//    The arithmetic follows numpy's evaluation order (sequential fp32 column sums, fp32 IEEE
+//    division) so that the result is bit-identical to the reference when the host supplies the
+//    same sample indices.
+//
+//  * confusion_count: argmax + confusion-matrix accumulation of the evaluation loops
+//    (learning/main.py:257-262,297-305; learning/metrics.py:16-18), integer, exact.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace spg {
+
+// counter-based generator for the device-side sampling / jitter option (no numpy parity by
+// construction: the reference draws from MT19937 on the host)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t bits) {  // (0,1]
+    return ((float)(bits >> 40) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+struct CloudBuildArgs {
+    const float* points;       // [rows, ldp] parsed point attributes of every resident superpoint
+    int64_t ldp;
+    const int64_t* sp_start;   // [Nv] first row of each selected superpoint
+    const int32_t* sp_count;   // [Nv] its number of points (>= 1)
+    const int32_t* sample_idx; // [Nv, L] source point of every output point, or null (device RNG)
+    const int32_t* columns;    // [F] source column of each output attribute
+    int F, L, normalize;
+    const double* xform;       // [Nv, 9] row-major 3x3 applied to output attributes 0..2, or null
+    const float* jitter;       // [Nv, L, F] additive noise (already clipped), or null
+    float jitter_sigma, jitter_clip;  // used when jitter == null and jitter_sigma > 0
+    uint64_t seed;
+    float* clouds;             // [Nv, F, L]
+    float* diameters;          // [Nv]
+};
+
+// One CTA per cloud.  smem: xyz[L][3] + 8 scalars.
+__global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a) {
+    extern __shared__ float sm[];
+    float* xyz = sm;                 // [L][3]
+    float* red = sm + 3 * a.L;       // mean[3], diameter, inv-denominator
+    const int64_t i = blockIdx.x;
+    const int L = a.L, F = a.F;
+    const int64_t start = a.sp_start[i];
+    const int n = a.sp_count[i];
+    auto src_row = [&](int j) -> int64_t {
+        int r;
+        if (a.sample_idx) {
+            r = a.sample_idx[i * L + j];
+        } else if (n == L || (n < L && j < n)) {
+            r = j;  // kept as is / the original points come first (spg.py:209-214)
+        } else {
+            r = (int)(mix64(a.seed ^ mix64((uint64_t)i * 0x100000001B3ull + (uint64_t)j)) % (uint64_t)n);
+        }
+        return start + r;
+    };
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const float* p = a.points + src_row(j) * a.ldp;
+        xyz[3 * j + 0] = p[0];
+        xyz[3 * j + 1] = p[1];
+        xyz[3 * j + 2] = p[2];
+    }
+    __syncthreads();
+    // numpy reduces a C-ordered [L,3] array over axis 0 row by row: plain sequential fp32 sums.
+    // lanes 0-2: sum, 3-5: min, 6-8: max of coordinate lane%3.
+    if (threadIdx.x < 9) {
+        const int k = threadIdx.x % 3, what = threadIdx.x / 3;
+        float v = xyz[k];
+        for (int j = 1; j < L; ++j) {
+            const float x = xyz[3 * j + k];
+            v = what == 0 ? v + x : (what == 1 ? fminf(v, x) : fmaxf(v, x));
+        }
+        red[3 * what + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float diam = 0.f;
+        if (a.normalize) {
+            diam = fmaxf(fmaxf(red[6] - red[3], red[7] - red[4]), red[8] - red[5]);
+        }
+        a.diameters[i] = diam;
+        red[9] = a.normalize ? (float)((double)diam + 1e-10) : 1.f;
+        red[0] = red[0] / (float)L;
+        red[1] = red[1] / (float)L;
+        red[2] = red[2] / (float)L;
+    }
+    __syncthreads();
+    const float den = red[9];
+    const bool norm = a.normalize;
+    const double* M = a.xform ? a.xform + i * 9 : nullptr;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const float* p = a.points + src_row(j) * a.ldp;
+        float c3[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float d = xyz[3 * j + k] - red[k];
+            c3[k] = norm ? __fdiv_rn(d, den) : d;
+        }
+        float o3[3] = {0.f, 0.f, 0.f};
+        for (int f = 0; f < F; ++f) {
+            const int c = a.columns[f];
+            float v = c < 3 ? c3[c] : p[c];
+            if (M && f < 3) {
+                o3[f] = v;
+                continue;  // written below, after the 3x3
+            }
+            if (a.jitter) {
+                v += a.jitter[(i * L + j) * F + f];
+            } else if (a.jitter_sigma > 0.f) {
+                const uint64_t h = mix64(a.seed ^ mix64(((uint64_t)i * L + j) * 64 + f + 0x5bd1e995ull));
+                const float g = sqrtf(-2.f * logf(u01(h))) * cospif(2.f * u01(mix64(h)));
+                v += fminf(fmaxf(a.jitter_sigma * g, -a.jitter_clip), a.jitter_clip);
+            }
+            a.clouds[(i * F + f) * L + j] = v;
+        }
+        if (M) {
+            // P[:, :3] = P[:, :3] . M^T in double, rounded once (spg.py:254)
+            const int nf = F < 3 ? F : 3;
+            for (int f = 0; f < nf; ++f) {
+                double acc = 0.0;
+                for (int k = 0; k < nf; ++k) acc += (double)o3[k] * M[3 * f + k];
+                float v = (float)acc;
+                if (a.jitter) {
+                    v += a.jitter[(i * L + j) * F + f];
+                } else if (a.jitter_sigma > 0.f) {
+                    const uint64_t h = mix64(a.seed ^ mix64(((uint64_t)i * L + j) * 64 + f + 0x5bd1e995ull));
+                    const float g = sqrtf(-2.f * logf(u01(h))) * cospif(2.f * u01(mix64(h)));
+                    v += fminf(fmaxf(a.jitter_sigma * g, -a.jitter_clip), a.jitter_clip);
+                }
+                a.clouds[(i * F + f) * L + j] = v;
+            }
+        }
+    }
+}
+
+// One warp per superpoint: pred = first argmax of its logits; nodes with a label add their
+// per-class point histogram to column `pred` of the confusion matrix.
+__global__ void __launch_bounds__(256)
+confusion_count_kernel(const float* __restrict__ logits, int64_t ldl,
+                       const int64_t* __restrict__ label_mode,
+                       const int64_t* __restrict__ label_vec, int64_t ldv,
+                       unsigned long long* __restrict__ cm, unsigned long long* __restrict__ counters,
+                       int64_t* __restrict__ pred_out, int64_t n, int C) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    float best = -FLT_MAX;
+    int arg = 0x7fffffff;
+    bool seen = false;
+    for (int c = lane; c < C; c += 32) {
+        const float v = logits[i * ldl + c];
+        if (!seen || v > best) {  // strict: keeps the first maximum within the lane
+            best = v;
+            arg = c;
+            seen = true;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) {
+            best = ob;
+            arg = oa;
+        }
+    }
+    if (lane == 0 && pred_out) pred_out[i] = arg;
+    const int64_t t = label_mode[i];
+    if (t == -100) return;  // no ground truth (main.py:447-452 filter_valid)
+    for (int c = lane; c < C; c += 32) {
+        const int64_t add = label_vec[i * ldv + c];
+        if (add != 0) atomicAdd(cm + (int64_t)c * C + arg, (unsigned long long)add);
+    }
+    if (lane == 0) {
+        atomicAdd(counters + 0, 1ull);
+        if (t == arg) atomicAdd(counters + 1, 1ull);
+    }
+}
+
+}  // namespace spg
+
+using namespace spg;
+
+extern "C" {
+
+int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
+                    const int32_t* sp_count, const int32_t* sample_idx, const int32_t* columns,
+                    int n_attribs, int n_points, int normalize, const double* xform,
+                    const float* jitter, float jitter_sigma, float jitter_clip, int64_t seed,
+                    float* clouds, float* diameters, int64_t n_clouds, spg_stream_t stream) {
+    if (n_clouds < 0 || n_attribs <= 0 || n_points <= 0 || ldp < 3) return SPG_E_BADARG;
+    if (n_clouds == 0) return SPG_OK;
+    if (!points || !sp_start || !sp_count || !columns || !clouds || !diameters) return SPG_E_BADARG;
+    const size_t smem = sizeof(float) * (3 * (size_t)n_points + 16);
+    if (smem > 200 * 1024 || n_clouds > 0x7fffffffll) return SPG_E_UNSUPPORTED;
+    CloudBuildArgs a;
+    a.points = points;
+    a.ldp = ldp;
+    a.sp_start = sp_start;
+    a.sp_count = sp_count;
+    a.sample_idx = sample_idx;
+    a.columns = columns;
+    a.F = n_attribs;
+    a.L = n_points;
+    a.normalize = normalize;
+    a.xform = xform;
+    a.jitter = jitter;
+    a.jitter_sigma = jitter_sigma;
+    a.jitter_clip = jitter_clip;
+    a.seed = (uint64_t)seed;
+    a.clouds = clouds;
+    a.diameters = diameters;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cloud_build_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    SPG_LAUNCH(K_CLOUD_BUILD, (cudaStream_t)stream, cloud_build_kernel, (unsigned)n_clouds, 128, smem,
+               a);
+    return launch_status();
+}
+
+int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* label_mode,
+                        const int64_t* label_vec, int64_t ld_vec, int64_t* confusion,
+                        int64_t* counters, int64_t* pred_out, int64_t n_nodes, int n_classes,
+                        spg_stream_t stream) {
+    if (n_nodes < 0 || n_classes <= 0) return SPG_E_BADARG;
+    if (n_nodes == 0) return SPG_OK;
+    if (!logits || !label_mode || !label_vec || !confusion || !counters) return SPG_E_BADARG;
+    const int64_t blocks = ceil_div64(n_nodes, 8);
+    SPG_LAUNCH(K_CONFUSION, (cudaStream_t)stream, confusion_count_kernel, (unsigned)blocks, 256, 0,
+               logits, ld_logits, label_mode, label_vec, ld_vec,
+               reinterpret_cast<unsigned long long*>(confusion),
+               reinterpret_cast<unsigned long long*>(counters), pred_out, n_nodes, n_classes);
+    return launch_status();
+}
+
+}  // extern "C"

@@ -572,3 +572,38 @@ def prof_collect():
 
 def total_launches():
     return int(_lib.lib().spg_prof_total_launches())
+
+
+# ------------------------------------------------------------- either side of the path
+def cloud_build(points, sp_start, sp_count, sample_idx, columns, n_points, normalize, xform, jitter,
+                jitter_sigma, jitter_clip, seed, clouds, diameters):
+    """Resample / normalise / select / augment superpoints straight into the [Nv, F, L] PointNet
+    input (ref: learning/spg.py:198-260); see include/spg_b200.h spg_cloud_build."""
+    _need_cuda(points, sp_start, sp_count, sample_idx, columns, xform, jitter, clouds, diameters)
+    assert points.dtype == torch.float32 and points.is_contiguous()
+    assert sp_start.dtype == torch.int64 and sp_count.dtype == torch.int32 and columns.dtype == torch.int32
+    assert sample_idx is None or (sample_idx.dtype == torch.int32 and sample_idx.is_contiguous())
+    assert xform is None or (xform.dtype == torch.float64 and xform.is_contiguous())
+    assert jitter is None or (jitter.dtype == torch.float32 and jitter.is_contiguous())
+    nv, F, L = clouds.shape
+    assert L == n_points and columns.numel() == F
+    _lib.call("spg_cloud_build", points, points.shape[1], sp_start, sp_count, sample_idx, columns, F,
+              L, int(bool(normalize)), xform, jitter, float(jitter_sigma), float(jitter_clip),
+              int(seed), clouds, diameters, nv, _lib.current_stream())
+    return clouds, diameters
+
+
+def confusion_count(logits, label_mode, label_vec, confusion, counters, want_predictions=False):
+    """confusion[:, argmax(logits_i)] += label_vec[i] for the labelled nodes (ref: learning/main.py:
+    257-262, metrics.py:16-18); returns the predictions of all nodes if asked."""
+    _need_cuda(logits, label_mode, label_vec, confusion, counters)
+    logits = _c(logits)
+    label_mode, label_vec = _c(label_mode), _c(label_vec)
+    n, C = logits.shape
+    assert logits.dtype == torch.float32 and label_mode.dtype == torch.int64
+    assert label_vec.dtype == torch.int64 and label_vec.shape == (n, C)
+    assert confusion.dtype == torch.int64 and confusion.shape == (C, C) and confusion.is_contiguous()
+    pred = torch.empty(n, dtype=torch.int64, device=logits.device) if want_predictions else None
+    _lib.call("spg_confusion_count", logits, C, label_mode, label_vec, C, confusion, counters, pred,
+              n, C, _lib.current_stream())
+    return pred

@@ -318,8 +318,96 @@ def train_steps():
     save("train_steps.npz", **arrs)
 
 
+
+# ----------------------------------------------------------------------------- batch loader
+class _FakeH5File(dict):
+    """Stand-in for h5py.File over an in-memory {dataset name: ndarray}: `load_superpoint` only
+    does `hf['<id>']`, `.shape[0]` and `[:]` (learning/spg.py:200-205)."""
+    store = {}
+
+    def __init__(self, fname, mode="r"):
+        super(_FakeH5File, self).__init__(_FakeH5File.store[fname])
+
+
+def _import_reference_spg():
+    for name in ("transforms3d", "h5py"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["h5py"].File = _FakeH5File
+    from learning import spg  # noqa: E402
+    return spg
+
+
+def loader_clouds():
+    """The reference's own `load_superpoint` (evaluation mode: per-superpoint RandomState, no
+    augmentation) on synthetic parsed superpoints of 1..700 points, two attribute selections."""
+    from types import SimpleNamespace
+    spg = _import_reference_spg()
+    rng = np.random.default_rng(31)
+    counts = [1, 39, 40, 41, 127, 128, 129, 300, 700, 64]
+    parsed = {}
+    for sid, n in enumerate(counts):
+        P = rng.standard_normal((n, 15)).astype(np.float32)
+        P[:, :3] = P[:, :3] * rng.uniform(0.2, 4.0) + rng.uniform(-20, 20, size=3)
+        P[:, 11:14] = rng.uniform(0, 1, size=(n, 3))
+        parsed["%d" % sid] = P
+    _FakeH5File.store = {"mem.h5": parsed}
+    out = {"counts": np.array(counts)}
+    for sid, P in parsed.items():
+        out["P%s" % sid] = P
+    cases = (("s3dis", "xyzrgbelpsvXYZ", 1, 128, 40, 0), ("sema", "xyzrgbelpsv", 1, 128, 40, 3),
+             ("nonorm", "xyzelpsv", 0, 64, 1, 0))
+    for tag, attribs, norm, npts, minpts, offset in cases:
+        args = SimpleNamespace(ptn_minpts=minpts, ptn_npts=npts, pc_xyznormalize=norm, pc_attribs=attribs)
+        flags, clouds, diams = [], [], []
+        for sid in range(len(counts)):
+            cloud, diam = spg.load_superpoint(args, "mem.h5", sid, False, offset)
+            flags.append(0 if cloud is not None else -1)
+            if cloud is not None:
+                clouds.append(cloud.T)
+                diams.append(diam)
+        out["%s_flag" % tag] = np.array(flags)
+        out["%s_clouds" % tag] = np.stack(clouds)
+        out["%s_global" % tag] = np.concatenate(diams)
+        out["%s_cfg" % tag] = np.array([norm, npts, minpts, offset])
+        out["%s_attribs" % tag] = np.array(attribs)
+    save("loader_clouds.npz", **out)
+
+
+def metrics_confusion():
+    """learning/metrics.py ConfusionMatrix driven as eval()/eval_final() do (main.py:257-262,297-305)."""
+    from learning import metrics
+    rng = np.random.default_rng(17)
+    C, out = 13, {}
+    cm = metrics.ConfusionMatrix(C)
+    for b, n in enumerate((50, 1, 333)):
+        o = rng.standard_normal((n, C)).astype(np.float32)
+        o[::7, 3] = o[::7, 5] = 9.0  # ties: argmax keeps the first
+        tvec = rng.integers(0, 400, size=(n, C)).astype(np.int64)
+        tvec[rng.random((n, C)) < 0.6] = 0
+        t = tvec.argmax(1)
+        t[rng.random(n) < 0.2] = -100
+        idx = t != -100
+        cm.count_predicted_batch(tvec[idx, ...], np.argmax(o[idx, :], 1))
+        out["o%d" % b], out["t%d" % b], out["tvec%d" % b] = o, t, tvec
+        out["pred%d" % b] = np.argmax(o, 1)
+    out["cm"] = cm.confusion_matrix.copy()
+    out["oa"] = np.array(cm.get_overall_accuracy())
+    out["miou"] = np.array(cm.get_average_intersection_union())
+    out["iou"] = np.array(cm.get_intersection_union_per_class())
+    out["macc"] = np.array(cm.get_mean_class_accuracy())
+    # multi-sample averaging of eval_final (main.py:292-295)
+    samples = [rng.standard_normal((40, C)).astype(np.float32) for _ in range(10)]
+    out["ms_samples"] = np.stack(samples, 0)
+    out["ms_mean"] = np.mean(np.stack(samples, 0), 0)
+    save("metrics_confusion.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if sys.argv[1:] == ["loader"]:  # only the section-8(f) fixtures
+        loader_clouds()
+        metrics_confusion()
+        sys.exit(0)
     ecc_unit_fixture()
     ecc_spg_shaped()
     gru_cell()
@@ -328,3 +416,5 @@ if __name__ == "__main__":
     graph_networks()
     shards()
     train_steps()
+    loader_clouds()
+    metrics_confusion()
