@@ -46,15 +46,18 @@ struct CloudBuildArgs {
     float* diameters;          // [Nv]
 };
 
-// One CTA per cloud.  smem: xyz[L][3] + 8 scalars.
+// One CTA per cloud.  The L sampled rows are staged once in shared memory (consecutive threads
+// read consecutive floats of a row, so a 60-byte row costs 2-3 sectors instead of one request per
+// attribute); everything else works on the staged copy.  smem: rows[L][ldp] + 16 scalars.
 __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a) {
     extern __shared__ float sm[];
-    float* xyz = sm;                 // [L][3]
-    float* red = sm + 3 * a.L;       // mean[3], diameter, inv-denominator
+    const int L = a.L, F = a.F, ldp = (int)a.ldp;
+    float* rows = sm;                  // [L][ldp]
+    float* red = sm + (size_t)L * ldp; // sum[3], min[3], max[3], denominator
     const int64_t i = blockIdx.x;
-    const int L = a.L, F = a.F;
     const int64_t start = a.sp_start[i];
     const int n = a.sp_count[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto src_row = [&](int j) -> int64_t {
         int r;
         if (a.sample_idx) {
@@ -66,30 +69,28 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
         }
         return start + r;
     };
-    for (int j = threadIdx.x; j < L; j += blockDim.x) {
-        const float* p = a.points + src_row(j) * a.ldp;
-        xyz[3 * j + 0] = p[0];
-        xyz[3 * j + 1] = p[1];
-        xyz[3 * j + 2] = p[2];
+    for (int e = threadIdx.x; e < L * ldp; e += blockDim.x) {
+        const int j = e / ldp, c = e - j * ldp;
+        rows[e] = __ldg(a.points + src_row(j) * a.ldp + c);
     }
     __syncthreads();
-    // numpy reduces a C-ordered [L,3] array over axis 0 row by row: plain sequential fp32 sums.
-    // lanes 0-2: sum, 3-5: min, 6-8: max of coordinate lane%3.
-    if (threadIdx.x < 9) {
-        const int k = threadIdx.x % 3, what = threadIdx.x / 3;
-        float v = xyz[k];
-        for (int j = 1; j < L; ++j) {
-            const float x = xyz[3 * j + k];
-            v = what == 0 ? v + x : (what == 1 ? fminf(v, x) : fmaxf(v, x));
+    // numpy reduces a C-ordered [L,3] array over axis 0 row by row: plain sequential fp32 sums
+    // (lanes 0-2 of warp 0); min and max are order-free (warps 1 and 2).
+    if (warp < 3 && lane < 3) {
+        float v = rows[lane];
+        if (warp == 0) {
+            for (int j = 1; j < L; ++j) v += rows[j * ldp + lane];
+        } else if (warp == 1) {
+            for (int j = 1; j < L; ++j) v = fminf(v, rows[j * ldp + lane]);
+        } else {
+            for (int j = 1; j < L; ++j) v = fmaxf(v, rows[j * ldp + lane]);
         }
-        red[3 * what + k] = v;
+        red[3 * warp + lane] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         float diam = 0.f;
-        if (a.normalize) {
-            diam = fmaxf(fmaxf(red[6] - red[3], red[7] - red[4]), red[8] - red[5]);
-        }
+        if (a.normalize) diam = fmaxf(fmaxf(red[6] - red[3], red[7] - red[4]), red[8] - red[5]);
         a.diameters[i] = diam;
         red[9] = a.normalize ? (float)((double)diam + 1e-10) : 1.f;
         red[0] = red[0] / (float)L;
@@ -100,12 +101,22 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
     const float den = red[9];
     const bool norm = a.normalize;
     const double* M = a.xform ? a.xform + i * 9 : nullptr;
+    auto noise = [&](int j, int f) -> float {
+        if (a.jitter) return a.jitter[(i * L + j) * F + f];
+        if (a.jitter_sigma > 0.f) {
+            const uint64_t h = mix64(a.seed ^ mix64(((uint64_t)i * L + j) * 64 + f + 0x5bd1e995ull));
+            const float g = sqrtf(-2.f * logf(u01(h))) * cospif(2.f * u01(mix64(h)));
+            return fminf(fmaxf(a.jitter_sigma * g, -a.jitter_clip), a.jitter_clip);
+        }
+        return 0.f;
+    };
+    const bool noisy = a.jitter || a.jitter_sigma > 0.f;
     for (int j = threadIdx.x; j < L; j += blockDim.x) {
-        const float* p = a.points + src_row(j) * a.ldp;
+        const float* p = rows + j * ldp;
         float c3[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float d = xyz[3 * j + k] - red[k];
+            const float d = p[k] - red[k];
             c3[k] = norm ? __fdiv_rn(d, den) : d;
         }
         float o3[3] = {0.f, 0.f, 0.f};
@@ -113,16 +124,10 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
             const int c = a.columns[f];
             float v = c < 3 ? c3[c] : p[c];
             if (M && f < 3) {
-                o3[f] = v;
-                continue;  // written below, after the 3x3
+                o3[f] = v;  // written below, after the 3x3
+                continue;
             }
-            if (a.jitter) {
-                v += a.jitter[(i * L + j) * F + f];
-            } else if (a.jitter_sigma > 0.f) {
-                const uint64_t h = mix64(a.seed ^ mix64(((uint64_t)i * L + j) * 64 + f + 0x5bd1e995ull));
-                const float g = sqrtf(-2.f * logf(u01(h))) * cospif(2.f * u01(mix64(h)));
-                v += fminf(fmaxf(a.jitter_sigma * g, -a.jitter_clip), a.jitter_clip);
-            }
+            if (noisy) v += noise(j, f);
             a.clouds[(i * F + f) * L + j] = v;
         }
         if (M) {
@@ -132,13 +137,7 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
                 double acc = 0.0;
                 for (int k = 0; k < nf; ++k) acc += (double)o3[k] * M[3 * f + k];
                 float v = (float)acc;
-                if (a.jitter) {
-                    v += a.jitter[(i * L + j) * F + f];
-                } else if (a.jitter_sigma > 0.f) {
-                    const uint64_t h = mix64(a.seed ^ mix64(((uint64_t)i * L + j) * 64 + f + 0x5bd1e995ull));
-                    const float g = sqrtf(-2.f * logf(u01(h))) * cospif(2.f * u01(mix64(h)));
-                    v += fminf(fmaxf(a.jitter_sigma * g, -a.jitter_clip), a.jitter_clip);
-                }
+                if (noisy) v += noise(j, f);
                 a.clouds[(i * F + f) * L + j] = v;
             }
         }
@@ -203,7 +202,7 @@ int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
     if (n_clouds < 0 || n_attribs <= 0 || n_points <= 0 || ldp < 3) return SPG_E_BADARG;
     if (n_clouds == 0) return SPG_OK;
     if (!points || !sp_start || !sp_count || !columns || !clouds || !diameters) return SPG_E_BADARG;
-    const size_t smem = sizeof(float) * (3 * (size_t)n_points + 16);
+    const size_t smem = sizeof(float) * ((size_t)n_points * (size_t)ldp + 16);
     if (smem > 200 * 1024 || n_clouds > 0x7fffffffll) return SPG_E_UNSUPPORTED;
     CloudBuildArgs a;
     a.points = points;
