@@ -46,18 +46,26 @@ struct CloudBuildArgs {
     float* diameters;          // [Nv]
 };
 
-// One CTA per cloud.  The L sampled rows are staged once in shared memory (consecutive threads
-// read consecutive floats of a row, so a 60-byte row costs 2-3 sectors instead of one request per
-// attribute); everything else works on the staged copy.  smem: rows[L][ldp] + 16 scalars.
-__global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a) {
+// One WARP per cloud (4 clouds per CTA): the kernel is a chain of dependent latencies (sample index
+// -> point row -> sequential column sums -> normalise -> store), so throughput comes from the number
+// of clouds in flight per SM (64 warps), not from the width of one cloud.  Only xyz is staged in
+// shared memory (the sums need it in order); the other attributes are re-read from the row, which is
+// in L1/L2 by then.  smem per warp: xyz[L][3] + 16 scalars; columns[F] once per CTA.
+constexpr int kCloudWarps = 4;
+
+__global__ void __launch_bounds__(kCloudWarps * 32) cloud_build_kernel(const CloudBuildArgs a, int64_t nv) {
     extern __shared__ float sm[];
-    const int L = a.L, F = a.F, ldp = (int)a.ldp;
-    float* rows = sm;                  // [L][ldp]
-    float* red = sm + (size_t)L * ldp; // sum[3], min[3], max[3], denominator
-    const int64_t i = blockIdx.x;
+    const int L = a.L, F = a.F;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* cols = reinterpret_cast<int*>(sm);                 // [F]
+    float* xyz = sm + F + (size_t)warp * (3 * L + 16);      // [L][3]
+    float* red = xyz + 3 * L;                               // sum[3], min[3], max[3], denominator
+    for (int f = threadIdx.x; f < F; f += blockDim.x) cols[f] = a.columns[f];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kCloudWarps + warp;
+    if (i >= nv) return;
     const int64_t start = a.sp_start[i];
     const int n = a.sp_count[i];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto src_row = [&](int j) -> int64_t {
         int r;
         if (a.sample_idx) {
@@ -69,26 +77,26 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
         }
         return start + r;
     };
-    for (int e = threadIdx.x; e < L * ldp; e += blockDim.x) {
-        const int j = e / ldp, c = e - j * ldp;
-        rows[e] = __ldg(a.points + src_row(j) * a.ldp + c);
+    for (int j = lane; j < L; j += 32) {
+        const float* p = a.points + src_row(j) * a.ldp;
+        xyz[3 * j + 0] = __ldg(p + 0);
+        xyz[3 * j + 1] = __ldg(p + 1);
+        xyz[3 * j + 2] = __ldg(p + 2);
     }
-    __syncthreads();
+    __syncwarp();
     // numpy reduces a C-ordered [L,3] array over axis 0 row by row: plain sequential fp32 sums
-    // (lanes 0-2 of warp 0); min and max are order-free (warps 1 and 2).
-    if (warp < 3 && lane < 3) {
-        float v = rows[lane];
-        if (warp == 0) {
-            for (int j = 1; j < L; ++j) v += rows[j * ldp + lane];
-        } else if (warp == 1) {
-            for (int j = 1; j < L; ++j) v = fminf(v, rows[j * ldp + lane]);
-        } else {
-            for (int j = 1; j < L; ++j) v = fmaxf(v, rows[j * ldp + lane]);
+    // (lanes 0-2); min and max are order-free (lanes 3-5, 6-8) and ride along in the same loop.
+    if (lane < 9) {
+        const int k = lane % 3, what = lane / 3;
+        float v = xyz[k];
+        for (int j = 1; j < L; ++j) {
+            const float x = xyz[3 * j + k];
+            v = what == 0 ? v + x : (what == 1 ? fminf(v, x) : fmaxf(v, x));
         }
-        red[3 * warp + lane] = v;
+        red[3 * what + k] = v;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncwarp();
+    if (lane == 0) {
         float diam = 0.f;
         if (a.normalize) diam = fmaxf(fmaxf(red[6] - red[3], red[7] - red[4]), red[8] - red[5]);
         a.diameters[i] = diam;
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
         red[1] = red[1] / (float)L;
         red[2] = red[2] / (float)L;
     }
-    __syncthreads();
+    __syncwarp();
     const float den = red[9];
     const bool norm = a.normalize;
     const double* M = a.xform ? a.xform + i * 9 : nullptr;
@@ -111,18 +119,18 @@ __global__ void __launch_bounds__(128) cloud_build_kernel(const CloudBuildArgs a
         return 0.f;
     };
     const bool noisy = a.jitter || a.jitter_sigma > 0.f;
-    for (int j = threadIdx.x; j < L; j += blockDim.x) {
-        const float* p = rows + j * ldp;
+    for (int j = lane; j < L; j += 32) {
+        const float* p = a.points + src_row(j) * a.ldp;
         float c3[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float d = p[k] - red[k];
+            const float d = xyz[3 * j + k] - red[k];
             c3[k] = norm ? __fdiv_rn(d, den) : d;
         }
         float o3[3] = {0.f, 0.f, 0.f};
         for (int f = 0; f < F; ++f) {
-            const int c = a.columns[f];
-            float v = c < 3 ? c3[c] : p[c];
+            const int c = cols[f];
+            float v = c < 3 ? c3[c] : __ldg(p + c);
             if (M && f < 3) {
                 o3[f] = v;  // written below, after the 3x3
                 continue;
@@ -202,7 +210,7 @@ int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
     if (n_clouds < 0 || n_attribs <= 0 || n_points <= 0 || ldp < 3) return SPG_E_BADARG;
     if (n_clouds == 0) return SPG_OK;
     if (!points || !sp_start || !sp_count || !columns || !clouds || !diameters) return SPG_E_BADARG;
-    const size_t smem = sizeof(float) * ((size_t)n_points * (size_t)ldp + 16);
+    const size_t smem = sizeof(float) * ((size_t)n_attribs + kCloudWarps * (3 * (size_t)n_points + 16));
     if (smem > 200 * 1024 || n_clouds > 0x7fffffffll) return SPG_E_UNSUPPORTED;
     CloudBuildArgs a;
     a.points = points;
@@ -226,8 +234,8 @@ int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    SPG_LAUNCH(K_CLOUD_BUILD, (cudaStream_t)stream, cloud_build_kernel, (unsigned)n_clouds, 128, smem,
-               a);
+    SPG_LAUNCH(K_CLOUD_BUILD, (cudaStream_t)stream, cloud_build_kernel,
+               (unsigned)ceil_div64(n_clouds, kCloudWarps), kCloudWarps * 32, smem, a, n_clouds);
     return launch_status();
 }
 

@@ -296,6 +296,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
 
 USE_TC = [os.environ.get("SPG_TC", "1") != "0"]  # tcgen05 path for the large point-wise layers
 USE_FUSED_RNN = [os.environ.get("SPG_FUSED_RNN", "1") != "0"]  # one-kernel R x {ECC, cell} loop
+USE_SIDE_STREAM = [os.environ.get("SPG_SIDE_STREAM", "1") != "0"]  # Trainer: block-local weight gradients on a 2nd stream
 
 
 def tc_supported(M, N, K, lda=0, ldc=0):
@@ -572,6 +573,37 @@ def prof_collect():
 
 def total_launches():
     return int(_lib.lib().spg_prof_total_launches())
+
+
+# ------------------------------------------------------------------ side stream (Trainer only)
+class SideStream(object):
+    """A second stream for work nobody waits for until the gradients are gathered: the filter-net
+    and cell weight gradients of the recurrent ECC block are chains of small, latency-bound kernels
+    that are independent of the (large) PointNet backward which follows them on the main stream.
+    `fork()` orders the side stream after everything enqueued so far, `join()` orders the current
+    stream after the side stream.  Tensors handed to fork() are kept alive until join(): the
+    caching allocator would otherwise recycle main-stream blocks the side kernels still read.
+    Only the Trainer installs one (SIDE[0]) — a caller who does not know about join() never forks."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep = []
+        self.active = False
+
+    def fork(self, *keep):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self.keep.append(keep)
+        self.active = True
+        return torch.cuda.stream(self.stream)
+
+    def join(self):
+        if self.active:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.active = False
+        self.keep = []
+
+
+SIDE = [None]
 
 
 # ------------------------------------------------------------- either side of the path

@@ -235,16 +235,32 @@ class _RecurrentECCFunction(torch.autograd.Function):
                 # and, with cat_all, the direct gradient of the concatenated output
                 gh = ops.ecc_bwd_x(weights, d_x, graph, H, add0=d_h,
                                    add1=None if gcat is None else gcat[r])
-        # filter gradient of all R steps in one pass
-        g_w = ops.ecc_bwd_w(hs[:R], ginp, graph, tuple(weights.shape), n_iter=R)
-        grads_f = [None] * n_fparams
-        chain_backward(g_w.view(E, -1), g_w.numel() // E, E, fspecs, fparams, fsaved, False,
-                       grads_f, own_g=True)
-        grads_c = _cell_weight_grads(flags, d_gi.view(R * N, 3 * H), d_gh.view(R * N, 3 * H),
-                                     d_q.view(R * N, H), xp.view(R * N, H), hs[:R].view(R * N, H),
-                                     dpre.view(R * N, 4 * H), R * N, H)
         g_hx = gh if ctx.needs_input_grad[0] else None
-        return (g_hx, None, None, None, None, None, None, None, None) + tuple(grads_f) + tuple(grads_c)
+
+        def parameter_grads():
+            # filter gradient of all R steps in one pass
+            g_w = ops.ecc_bwd_w(hs[:R], ginp, graph, tuple(weights.shape), n_iter=R)
+            grads_f = [None] * n_fparams
+            chain_backward(g_w.view(E, -1), g_w.numel() // E, E, fspecs, fparams, fsaved, False,
+                           grads_f, own_g=True)
+            grads_c = _cell_weight_grads(flags, d_gi.view(R * N, 3 * H), d_gh.view(R * N, 3 * H),
+                                         d_q.view(R * N, H), xp.view(R * N, H),
+                                         hs[:R].view(R * N, H), dpre.view(R * N, 4 * H), R * N, H)
+            return tuple(grads_f) + tuple(grads_c)
+
+        side = ops.SIDE[0]
+        if side is None:
+            return (g_hx, None, None, None, None, None, None, None, None) + parameter_grads()
+        # Trainer mode: the parameter gradients of this block do not feed anything upstream, so
+        # they run on the side stream underneath the PointNet backward that follows.  They are
+        # written to .grad here (the autograd engine must not touch tensors another stream is
+        # still producing); Trainer.compute_gradients joins the stream before it reads them.
+        with side.fork(hs, inps, weights, ginp, d_gi, d_gh, d_q, xp, dpre, fsaved, gout):
+            grads = parameter_grads()
+            for prm, g in zip(params, grads):
+                if g is not None and prm.requires_grad:
+                    prm.grad = g if prm.grad is None else prm.grad + g
+        return (g_hx,) + (None,) * (8 + len(params))
 
 
 class ECC_CRFModule(nn.Module):

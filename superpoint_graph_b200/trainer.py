@@ -126,6 +126,7 @@ class Trainer(object):
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
         self._learned_packs = {}  # weight images packed on demand by earlier steps (see compute_gradients)
+        self._side = ops.SideStream(self.flat.device) if (self.flat.is_cuda and ops.USE_SIDE_STREAM[0]) else None
         self.step_dev = torch.zeros((), dtype=torch.int64, device=self.flat.device)
         self._graphs = {}
         self.class_weights = class_weights
@@ -150,13 +151,17 @@ class Trainer(object):
         # classifier) is learned from the on-demand packs of the previous step -> one launch
         self._prepack(db)
         ops.PACK_LEARN[0] = self._learned_packs
+        ops.SIDE[0] = self._side
         try:
             logits = self.forward(db)
             loss, d_logits = ops.ce_loss(logits, db.labels, self.class_weights, -100)
             logits.backward(d_logits)
+            self.embedder.bw_hook()
         finally:
             ops.PACK_LEARN[0] = None
-        self.embedder.bw_hook()
+            ops.SIDE[0] = None
+            if self._side is not None:
+                self._side.join()
         ops.PACK_CACHE.clear()  # the optimizer is about to change the weights
         torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_grad)
         return loss, logits.detach()
