@@ -304,7 +304,10 @@ def loader_roofline(dev, pk, with_cpu):
     counts = rng.integers(40, 601, size=nv)
     starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
     host_pts = rng.standard_normal((int(counts.sum()), C), dtype=np.float32)
-    pts = torch.from_numpy(host_pts).to(dev)
+    padded = np.zeros((host_pts.shape[0], 16), np.float32)  # SuperpointStore's device layout
+    padded[:, :C] = host_pts
+    pts = torch.from_numpy(padded).to(dev)
+    del padded
     idx = (rng.random((nv, L)) * counts[:, None]).astype(np.int32)
     cols = attrib_columns("xyzrgbelpsvXYZ", C)
     F = len(cols)

@@ -77,11 +77,21 @@ __global__ void __launch_bounds__(kCloudWarps * 32) cloud_build_kernel(const Clo
         }
         return start + r;
     };
+    // rows padded to a multiple of 4 floats (SuperpointStore does that) are fetched with 128-bit
+    // loads: 1 + ldp/4 requests per point instead of 3 + F
+    const bool vec = (a.ldp & 3) == 0 && a.ldp <= 16 && (reinterpret_cast<uintptr_t>(a.points) & 15) == 0;
     for (int j = lane; j < L; j += 32) {
         const float* p = a.points + src_row(j) * a.ldp;
-        xyz[3 * j + 0] = __ldg(p + 0);
-        xyz[3 * j + 1] = __ldg(p + 1);
-        xyz[3 * j + 2] = __ldg(p + 2);
+        if (vec) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+            xyz[3 * j + 0] = q.x;
+            xyz[3 * j + 1] = q.y;
+            xyz[3 * j + 2] = q.z;
+        } else {
+            xyz[3 * j + 0] = __ldg(p + 0);
+            xyz[3 * j + 1] = __ldg(p + 1);
+            xyz[3 * j + 2] = __ldg(p + 2);
+        }
     }
     __syncwarp();
     // numpy reduces a C-ordered [L,3] array over axis 0 row by row: plain sequential fp32 sums
@@ -127,10 +137,24 @@ __global__ void __launch_bounds__(kCloudWarps * 32) cloud_build_kernel(const Clo
             const float d = xyz[3 * j + k] - red[k];
             c3[k] = norm ? __fdiv_rn(d, den) : d;
         }
+        float4 q0, q1, q2, q3;
+        q0 = q1 = q2 = q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+            q0 = __ldg(p4);
+            if (a.ldp > 4) q1 = __ldg(p4 + 1);
+            if (a.ldp > 8) q2 = __ldg(p4 + 2);
+            if (a.ldp > 12) q3 = __ldg(p4 + 3);
+        }
+        auto pick = [&](int c) -> float {  // register select, no local-memory indexing
+            const float4 q = c < 8 ? (c < 4 ? q0 : q1) : (c < 12 ? q2 : q3);
+            const int k = c & 3;
+            return k < 2 ? (k == 0 ? q.x : q.y) : (k == 2 ? q.z : q.w);
+        };
         float o3[3] = {0.f, 0.f, 0.f};
         for (int f = 0; f < F; ++f) {
             const int c = cols[f];
-            float v = c < 3 ? c3[c] : __ldg(p + c);
+            float v = c < 3 ? c3[c] : (vec ? pick(c) : __ldg(p + c));
             if (M && f < 3) {
                 o3[f] = v;  // written below, after the 3x3
                 continue;

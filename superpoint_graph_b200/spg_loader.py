@@ -62,8 +62,15 @@ class SuperpointStore(object):
             self._rows += P.shape[0]
 
     def finalize(self, device):
-        host = (np.concatenate(self._chunks, 0) if self._chunks
-                else np.zeros((0, self.n_columns or 3), np.float32))
+        """Uploads the packed array.  Rows are padded with zeros to a multiple of 4 floats so that
+        the kernel fetches a point with 128-bit loads (15 parsed columns -> 64-byte rows)."""
+        nc = self.n_columns or 3
+        ld = (nc + 3) // 4 * 4
+        host = np.zeros((self._rows, ld), np.float32)
+        r = 0
+        for P in self._chunks:
+            host[r:r + P.shape[0], :nc] = P
+            r += P.shape[0]
         self.points = torch.from_numpy(host).to(device)
         self._chunks = []
         return self

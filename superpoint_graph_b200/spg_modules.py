@@ -148,6 +148,20 @@ class RNNGraphConvModule(nn.Module):
 
     def set_info(self, gc_info):
         self._gci = gc_info
+        self._prefetched = None
+
+    def prefetch_filters(self):
+        """Trainer only (needs ops.SIDE): evaluate the filter network now, on the side stream —
+        it depends on the edge features alone, so it can run underneath the PointNet forward
+        instead of after it.  forward() picks the result up and joins the stream."""
+        side = ops.SIDE[0]
+        if side is None or self._gci is None:
+            return
+        edgefeats = self._gci.get_buffers()[4]
+        fspecs, fparams = parse_sequential(self._fnet, self.training)
+        with side.fork(edgefeats):
+            self._prefetched = (self._gci, self.training) + _filter_bank(edgefeats, fspecs, fparams,
+                                                                         self.training)
 
     def forward(self, hx):
         idxn, idxe, degs, degs_gpu, edgefeats = self._gci.get_buffers()
@@ -155,28 +169,41 @@ class RNNGraphConvModule(nn.Module):
         cell = self._cell
         fspecs, fparams = parse_sequential(self._fnet, self.training)
         cparams = [q for q in cell.cell_params() if q is not None]
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None:
+            if pre[0] is not self._gci or pre[1] != self.training or ops.SIDE[0] is None:
+                raise RuntimeError("prefetch_filters() result does not belong to this forward")
+            ops.SIDE[0].join()
+            pre = pre[2:]
         return _RecurrentECCFunction.apply(hx, edgefeats, graph, fspecs, len(fparams), cell.flags(),
-                                           self._nrepeats, self._cat_all, self.training,
+                                           self._nrepeats, self._cat_all, self.training, pre,
                                            *(fparams + cparams))
+
+
+def _filter_bank(edgefeats, fspecs, fparams, training):
+    """fnet(edgefeats) -> (weights [E, width], saved activations, pending BN state)."""
+    edgefeats = edgefeats.contiguous()
+    if edgefeats.dtype != torch.float32:
+        edgefeats = edgefeats.float()
+    E, Fe = edgefeats.shape
+    fsaved = [] if training else None
+    wdef = chain_forward(Deferred(edgefeats, Fe, Fe), E, fspecs, fparams, training, fsaved)
+    return wdef.materialise(E), fsaved, wdef.pending
 
 
 class _RecurrentECCFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hx, edgefeats, graph, fspecs, n_fparams, flags, nrepeats, cat_all, training,
-                *params):
+                pre, *params):
         fparams, cpresent = params[:n_fparams], params[n_fparams:]
         hx = hx.contiguous()
-        edgefeats = edgefeats.contiguous()
-        if edgefeats.dtype != torch.float32:
-            edgefeats = edgefeats.float()
         N, H = hx.shape
-        E, Fe = edgefeats.shape
+        E = edgefeats.shape[0]
         dev = hx.device
-        # 1) filter bank, once
-        fsaved = [] if training else None
-        wdef = chain_forward(Deferred(edgefeats, Fe, Fe), E, fspecs, fparams, training, fsaved)
-        weights = wdef.materialise(E)
+        # 1) filter bank, once (possibly evaluated ahead of time on the side stream)
+        weights, fsaved, w_pending = pre if pre is not None else _filter_bank(edgefeats, fspecs,
+                                                                              fparams, training)
         assert weights.size(1) in (H, H * H)
         if weights.size(1) != H:
             weights = weights.view(E, H, H)
@@ -196,7 +223,7 @@ class _RecurrentECCFunction(torch.autograd.Function):
         if training:
             ctx.save_for_backward(hs, inps, weights)
         ctx.meta = (graph, fspecs, n_fparams, flags, nrepeats, cat_all, training, fsaved,
-                    wdef.pending, params, N, H, E)
+                    w_pending, params, N, H, E)
         if cat_all:
             return hs.permute(1, 0, 2).reshape(N, (nrepeats + 1) * H)
         return hs[nrepeats].clone()
@@ -250,7 +277,7 @@ class _RecurrentECCFunction(torch.autograd.Function):
 
         side = ops.SIDE[0]
         if side is None:
-            return (g_hx, None, None, None, None, None, None, None, None) + parameter_grads()
+            return (g_hx, None, None, None, None, None, None, None, None, None) + parameter_grads()
         # Trainer mode: the parameter gradients of this block do not feed anything upstream, so
         # they run on the side stream underneath the PointNet backward that follows.  They are
         # written to .grad here (the autograd engine must not touch tensors another stream is
@@ -260,7 +287,7 @@ class _RecurrentECCFunction(torch.autograd.Function):
             for prm, g in zip(params, grads):
                 if g is not None and prm.requires_grad:
                     prm.grad = g if prm.grad is None else prm.grad + g
-        return (g_hx,) + (None,) * (8 + len(params))
+        return (g_hx,) + (None,) * (9 + len(params))
 
 
 class ECC_CRFModule(nn.Module):

@@ -137,6 +137,10 @@ class Trainer(object):
 
     def forward(self, db):
         self.model.ecc.gconvs[0].set_info(db.gi)
+        if ops.SIDE[0] is not None:  # filter networks run underneath the PointNet forward
+            for gc in self.model.ecc.gconvs:
+                if hasattr(gc, "prefetch_filters"):
+                    gc.prefetch_filters()
         out = self.model.ptn(db.clouds, db.clouds_global)
         emb = _scatter(out, db.idx_valid, db.n_nodes)
         return self.model.ecc(emb)

@@ -225,3 +225,28 @@ def test_confusion_count_matches_reference_exactly():
     for s in m["ms_samples"]:
         ms.add(torch.from_numpy(s).to(dev))
     assert np.array_equal(ms.value().cpu().numpy(), m["ms_mean"])
+
+
+@pytest.mark.gpu
+def test_cloud_build_unpadded_rows_take_the_scalar_path():
+    """The C-ABI accepts any row pitch; 15-float rows (the parsed files as they are) cannot be
+    fetched with 128-bit loads and go through the scalar path — same bits."""
+    from superpoint_graph_b200 import ops
+    dev = torch.device("cuda:0")
+    g = _gold("loader_clouds.npz")
+    args, off = _case(g, "s3dis")
+    ids = [sid for sid, n in enumerate(g["counts"]) if n >= args.ptn_minpts]
+    pts = np.concatenate([g["P%d" % sid] for sid in ids], 0)
+    counts = np.array([g["counts"][sid] for sid in ids])
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    idx = np.stack([lr.sample_indices(int(g["counts"][sid]), 128, lr.test_rng(sid, off)) for sid in ids])
+    cols = lr.attrib_columns(args.pc_attribs)
+    clouds = torch.empty((len(ids), len(cols), 128), device=dev)
+    diam = torch.empty(len(ids), device=dev)
+    ops.cloud_build(torch.from_numpy(pts).to(dev), torch.from_numpy(starts.astype(np.int64)).to(dev),
+                    torch.from_numpy(counts.astype(np.int32)).to(dev),
+                    torch.from_numpy(idx.astype(np.int32)).to(dev),
+                    torch.tensor(cols, dtype=torch.int32, device=dev), 128, True, None, None, 0.0, 0.05, 0,
+                    clouds, diam)
+    assert np.array_equal(clouds.cpu().numpy(), g["s3dis_clouds"])
+    assert np.array_equal(diam.cpu().numpy(), g["s3dis_global"])
