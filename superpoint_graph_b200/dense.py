@@ -166,6 +166,11 @@ def chain_forward(inp, M, specs, params, training, saved=None):
     return cur
 
 
+def _accumulate_grad(prm, g):
+    if prm.requires_grad:
+        prm.grad = g if prm.grad is None else prm.grad + g
+
+
 def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_g=False, pooled=None):
     """G: gradient w.r.t. the chain's final *activated* output [M, C_last].
     `grads` (list aligned with params) is filled in place.  Returns the gradient w.r.t. the
@@ -208,22 +213,42 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
             dY, ldy = G, ldg
         # weight gradient: dW[cout, cin] = dY^T [cout, M] * act(prev)[M, cin]
         Wp = params[sp.w]
-        kpad = _padded_k(sp.cin, cur.ld)
-        if ops.tc_dw_supported(M, sp.cout, kpad, ldy, cur.ld) and (kpad == sp.cin or not cur.pending):
-            dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, kpad, p_aff=cur.aff())
-            if kpad != sp.cin:
-                dW = dW[:, :sp.cin].contiguous()
-        else:
-            dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
-        grads[sp.w] = dW.view(Wp.shape)
-        if sp.b is not None:
-            if sp.bn is not None and nxt.scale is not None and mean is not None:
-                # a bias that feeds a batch-statistics BatchNorm has an analytically zero
-                # gradient (sum_m dY = -scale*s2/M * sum_m xhat = 0); the reference holds rounding
-                # noise there.  No reduction is launched.
-                grads[sp.b] = _zeros(C, dY.device)
+
+        def weight_grads(dY=dY, ldy=ldy, cur=cur, nxt=nxt, mean=mean, sp=sp, Wp=Wp, C=C):
+            kpad = _padded_k(sp.cin, cur.ld)
+            if ops.tc_dw_supported(M, sp.cout, kpad, ldy, cur.ld) and (kpad == sp.cin or not cur.pending):
+                dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, kpad, p_aff=cur.aff())
+                if kpad != sp.cin:
+                    dW = dW[:, :sp.cin].contiguous()
             else:
-                grads[sp.b] = ops.colsum(dY, ldy, M, C)
+                dW = ops.gemm(dY, ldy, False, cur.raw, cur.ld, False, sp.cout, sp.cin, M, b_aff=cur.aff())
+            db = None
+            if sp.b is not None:
+                if sp.bn is not None and nxt.scale is not None and mean is not None:
+                    # a bias that feeds a batch-statistics BatchNorm has an analytically zero
+                    # gradient (sum_m dY = -scale*s2/M * sum_m xhat = 0); the reference holds
+                    # rounding noise there.  No reduction is launched.
+                    db = _zeros(C, dY.device)
+                else:
+                    db = ops.colsum(dY, ldy, M, C)
+            return dW.view(Wp.shape), db
+
+        side = ops.SIDE[0]
+        if side is None:
+            grads[sp.w], db = weight_grads()
+            if sp.b is not None:
+                grads[sp.b] = db
+        else:
+            # Trainer mode: nothing downstream reads a weight gradient, so it runs on the side
+            # stream while this stream goes on with the data gradient and the next layer.  The
+            # result goes straight to .grad (see _RecurrentECCFunction.backward).
+            with side.fork(dY, saved[li]):
+                dW, db = weight_grads()
+                _accumulate_grad(Wp, dW)
+                if sp.b is not None:
+                    if db is _ZEROS.get((C, dY.device.index)):
+                        db = db.clone()  # .grad must not alias the shared zero vector
+                    _accumulate_grad(params[sp.b], db)
         if li > 0 or need_input_grad:
             if ops.tc_supported(M, sp.cin, sp.cout, ldy, sp.cin):
                 G = ops.tc_gemm(dY, ldy, _w2d(Wp), sp.cin, True, M, sp.cin, sp.cout)
