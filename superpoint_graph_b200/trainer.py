@@ -127,6 +127,8 @@ class Trainer(object):
         self.step_count = 0
         self._learned_packs = {}  # weight images packed on demand by earlier steps (see compute_gradients)
         self._side = ops.SideStream(self.flat.device) if (self.flat.is_cuda and ops.USE_SIDE_STREAM[0]) else None
+        self._capturing = False
+        self.side_in_eager = False  # tests: exercise the two-stream schedule without a graph
         self.step_dev = torch.zeros((), dtype=torch.int64, device=self.flat.device)
         self._graphs = {}
         self.class_weights = class_weights
@@ -155,7 +157,10 @@ class Trainer(object):
         # classifier) is learned from the on-demand packs of the previous step -> one launch
         self._prepack(db)
         ops.PACK_LEARN[0] = self._learned_packs
-        ops.SIDE[0] = self._side
+        # the second stream pays off where the GPU is the bottleneck (graph replay); eager steps are
+        # bound by the CPU issuing ~250 launches, and every fork costs host time
+        use_side = self._side is not None and (self._capturing or self.side_in_eager)
+        ops.SIDE[0] = self._side if use_side else None
         try:
             logits = self.forward(db)
             loss, d_logits = ops.ce_loss(logits, db.labels, self.class_weights, -100)
@@ -164,7 +169,7 @@ class Trainer(object):
         finally:
             ops.PACK_LEARN[0] = None
             ops.SIDE[0] = None
-            if self._side is not None:
+            if use_side:
                 self._side.join()
         ops.PACK_CACHE.clear()  # the optimizer is about to change the weights
         torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_grad)
@@ -206,8 +211,12 @@ class Trainer(object):
         ops.PACK_CACHE.clear()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            loss, logits = self.compute_gradients(db)
+        self._capturing = True
+        try:
+            with torch.cuda.graph(g):
+                loss, logits = self.compute_gradients(db)
+        finally:
+            self._capturing = False
         self._graphs[key] = (g, db, loss, logits)
         return key
 

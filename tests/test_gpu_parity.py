@@ -664,6 +664,7 @@ def test_side_stream_gives_identical_steps(dev, monkeypatch, graph):
         model.to(dev)
         tr = Trainer(model, args)
         assert (tr._side is not None) == side
+        tr.side_in_eager = True  # default: only captured steps use the second stream
         db = HostBatch(batch).to_device(dev)
         losses = []
         if graph:
