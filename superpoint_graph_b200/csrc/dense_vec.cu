@@ -11,6 +11,35 @@ constexpr int kVecRows = 256;
 
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// Lane mapping shared by all kernels of this file.  A row of C floats is C/4 float4 lanes; for
+// C >= 128 a warp spans 128 columns of one row, for narrower power-of-two rows (C = 64, 32, ...)
+// the warp is folded over 32/(C/4) consecutive rows so that no lane idles (half of the PointNet
+// layers are 64 wide).  x: float4 column lane, sub: row within the warp's row group.
+struct LaneMap {
+    int cpl;   // float4 lanes per row handled by one warp
+    int rpw;   // rows per warp step
+    int x, sub;
+};
+__device__ __forceinline__ LaneMap lane_map(int C) {
+    LaneMap m;
+    const int lane = threadIdx.x & 31;
+    const int q = C >> 2;
+    m.cpl = (q < 32 && (q & (q - 1)) == 0) ? q : 32;
+    m.rpw = 32 / m.cpl;
+    m.x = lane % m.cpl;
+    m.sub = lane / m.cpl;
+    return m;
+}
+__device__ __forceinline__ float4 fold_rows(float4 a, int cpl) {
+    for (int o = cpl; o < 32; o <<= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    return a;
+}
+
 __global__ void __launch_bounds__(256)
 act_bwd_reduce_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ Y,
                          int64_t ldy, const float* __restrict__ scale,
@@ -18,7 +47,8 @@ act_bwd_reduce_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* 
                          const float* __restrict__ var, float eps, int relu,
                          float* __restrict__ ws, int64_t M, int C) {
     __shared__ float4 s1[8][32], s2[8][32];
-    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const LaneMap lm = lane_map(C);
+    const int x = lm.x, y = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + x) * 4;
     const int64_t r0 = (int64_t)blockIdx.y * kVecRows;
     const int64_t r1 = min(M, r0 + kVecRows);
@@ -31,7 +61,7 @@ act_bwd_reduce_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* 
         const float4 rs = make_float4(1.f / sqrtf(vr.x + eps), 1.f / sqrtf(vr.y + eps),
                                       1.f / sqrtf(vr.z + eps), 1.f / sqrtf(vr.w + eps));
 #pragma unroll 4
-        for (int64_t r = r0 + y; r < r1; r += 8) {
+        for (int64_t r = r0 + y * lm.rpw + lm.sub; r < r1; r += 8 * lm.rpw) {
             const float4 yv = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
             float4 g = __ldg(reinterpret_cast<const float4*>(G + r * ldg + c));
             if (relu) {
@@ -47,10 +77,12 @@ act_bwd_reduce_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* 
             a2.w = fmaf(g.w, (yv.w - mu.w) * rs.w, a2.w);
         }
     }
-    s1[y][x] = a1;
-    s2[y][x] = a2;
+    a1 = fold_rows(a1, lm.cpl);
+    a2 = fold_rows(a2, lm.cpl);
+    s1[y][threadIdx.x & 31] = a1;
+    s2[y][threadIdx.x & 31] = a2;
     __syncthreads();
-    if (y == 0 && c < C) {
+    if (y == 0 && lm.sub == 0 && c < C) {
         float4 t1 = f4zero(), t2 = f4zero();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -67,21 +99,23 @@ __global__ void __launch_bounds__(256)
 colsum_v4_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int C,
                  float* __restrict__ ws) {
     __shared__ float4 s[8][32];
-    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const LaneMap lm = lane_map(C);
+    const int x = lm.x, y = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + x) * 4;
     const int64_t r0 = (int64_t)blockIdx.y * kVecRows;
     const int64_t r1 = min(M, r0 + kVecRows);
     float4 a = f4zero();
     if (c < C) {
 #pragma unroll 4
-        for (int64_t r = r0 + y; r < r1; r += 8) {
+        for (int64_t r = r0 + y * lm.rpw + lm.sub; r < r1; r += 8 * lm.rpw) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(X + r * ldx + c));
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
     }
-    s[y][x] = a;
+    a = fold_rows(a, lm.cpl);
+    s[y][threadIdx.x & 31] = a;
     __syncthreads();
-    if (y == 0 && c < C) {
+    if (y == 0 && lm.sub == 0 && c < C) {
         float4 t = f4zero();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -112,7 +146,9 @@ act_bwd_apply_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* _
                         const float* __restrict__ var, float eps, int relu, int has_bn,
                         const float* __restrict__ s1, const float* __restrict__ s2,
                         float* __restrict__ dY, int64_t lddy, int64_t M, int C) {
-    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const LaneMap lm = lane_map(C);
+    const int x = lm.x, y = (threadIdx.x >> 5) * lm.rpw + lm.sub;
+    const int rows_per_block = 8 * lm.rpw;
     const int c = (blockIdx.x * 32 + x) * 4;
     if (c >= C) return;
     float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -130,7 +166,8 @@ act_bwd_apply_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* _
         }
     }
 #pragma unroll 4
-    for (int64_t r = (int64_t)blockIdx.y * 8 + y; r < M; r += (int64_t)gridDim.y * 8) {
+    for (int64_t r = (int64_t)blockIdx.y * rows_per_block + y; r < M;
+         r += (int64_t)gridDim.y * rows_per_block) {
         float4 yq = f4zero();
         if (Y) yq = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
         const float4 gq = __ldg(reinterpret_cast<const float4*>(G + r * ldg + c));
@@ -150,7 +187,9 @@ __global__ void __launch_bounds__(256)
 affine_act_v4_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                      const float* __restrict__ shift, int relu, float* __restrict__ out,
                      int64_t ldo, int64_t M, int C) {
-    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const LaneMap lm = lane_map(C);
+    const int x = lm.x, y = (threadIdx.x >> 5) * lm.rpw + lm.sub;
+    const int rows_per_block = 8 * lm.rpw;
     const int c = (blockIdx.x * 32 + x) * 4;
     if (c >= C) return;
     float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -160,7 +199,8 @@ affine_act_v4_kernel(const float* __restrict__ Y, int64_t ldy, const float* __re
         if (shift) sh[j] = shift[c + j];
     }
 #pragma unroll 4
-    for (int64_t r = (int64_t)blockIdx.y * 8 + y; r < M; r += (int64_t)gridDim.y * 8) {
+    for (int64_t r = (int64_t)blockIdx.y * rows_per_block + y; r < M;
+         r += (int64_t)gridDim.y * rows_per_block) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
         float v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll

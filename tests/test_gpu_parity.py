@@ -235,10 +235,12 @@ def test_gemm_prologues_and_reduction(dev):
     close(out, ref, 1e-5)
 
 
-def test_batch_stats_and_bn_backward(dev):
+@pytest.mark.parametrize("M,C", [(5000, 70), (4999, 64), (1031, 32), (777, 16), (3000, 96), (2500, 256)])
+def test_batch_stats_and_bn_backward(dev, M, C):
+    """C = 70: scalar kernels; C % 4 == 0: 128-bit kernels, with the warp folded over several rows
+    for the narrow power-of-two widths (64, 32, 16) and spanning 128 columns otherwise."""
     from superpoint_graph_b200 import ops
     torch.manual_seed(2)
-    M, C = 5000, 70
     Y = (torch.randn(M, C, dtype=torch.float64) * 3 + 100)  # large mean: cancellation-prone
     Yf = Y.float().to(dev)
     mean, var = ops.colstats(Yf, C, M, C)
