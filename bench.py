@@ -191,13 +191,26 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload="S3DIS-shaped training step, gru_10_1_1_1_0,f_13, fp32", **counts),
+        "config": dict(workload=workload_name(args.nodes), **counts),
+        "rates": rates(counts, 1, dt * 1e3),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d full training steps of the same batch (oracle/nets_ref.RefTrainer, "
                                    "ecc_mode=loop)" % args.steps},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def workload_name(nodes):
+    return ("configs[1]: S3DIS-shaped training step, gru_10_1_1_1_0,f_13, fp32, "
+            "2 scenes x %d superpoints per GPU" % (nodes // 2))
+
+
+def rates(counts, world, ms_per_step):
+    """the metric's components, whole job."""
+    k = world / (ms_per_step * 1e-3)
+    return {"superpoints_per_s": counts["superpoints"] * k, "points_per_s": counts["points"] * k,
+            "edges_per_s": counts["edges"] * k, "edge_iterations_per_s": counts["edges"] * 10 * k}
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -499,13 +512,13 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload="configs[1]: S3DIS-shaped training step, gru_10_1_1_1_0,f_13, fp32, "
-                                "2 scenes x %d superpoints per GPU" % (args.nodes // 2),
+        "config": dict(workload=workload_name(args.nodes),
                        parallelism="scene-parallel dp%d, one NCCL all-reduce of the flat gradient per step" % world,
                        l2="256 MiB memset between timed steps (outside the event brackets); 4 rotating batches",
                        **counts),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(t2) / args.steps},
+        "rates": rates(counts, world, total_ms / args.steps),
         "gpu_launches": int(launches),
         "cuda_graph": graph_keys is not None,
         "eager": {"ms_per_step": eager_ms, "value": eager_value},
