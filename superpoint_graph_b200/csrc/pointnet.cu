@@ -90,6 +90,65 @@ segmax_fwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restr
     }
 }
 
+// 128-bit variant: a warp spans 128 columns (float4 per lane), 8 row lanes, 4 rows in flight per
+// thread.  grid (ceil(C/128), B); block 256.  Same tie rule as the scalar kernel (first maximum).
+__global__ void __launch_bounds__(256)
+segmax_fwd_v4_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
+                     const float* __restrict__ shift, int relu, float* __restrict__ pooled,
+                     int64_t ldp, int* __restrict__ argmax, int L, int C) {
+    __shared__ float4 s_v[8][32];
+    __shared__ int4 s_i[8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + x) * 4;
+    const int64_t b = blockIdx.y;
+    float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int bi[4] = {-1, -1, -1, -1};
+    if (c < C) {
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (scale) sc[j] = scale[c + j];
+            if (shift) sh[j] = shift[c + j];
+        }
+        const float* src = Y + b * L * ldy + c;
+#pragma unroll 4
+        for (int l = y; l < L; l += 8) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src + (int64_t)l * ldy));
+            const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float t = fmaf(v[j], sc[j], sh[j]);
+                if (relu) t = fmaxf(t, 0.f);
+                if (bi[j] < 0 || t > best[j]) {  // first element initialises; strict > keeps first max
+                    best[j] = t;
+                    bi[j] = l;
+                }
+            }
+        }
+    }
+    s_v[y][x] = make_float4(best[0], best[1], best[2], best[3]);
+    s_i[y][x] = make_int4(bi[0], bi[1], bi[2], bi[3]);
+    __syncthreads();
+    if (y == 0 && c < C) {
+        for (int j = 1; j < 8; ++j) {
+            const float4 vq = s_v[j][x];
+            const int4 iq = s_i[j][x];
+            const float v[4] = {vq.x, vq.y, vq.z, vq.w};
+            const int i[4] = {iq.x, iq.y, iq.z, iq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i[k] >= 0 && (bi[k] < 0 || v[k] > best[k] || (v[k] == best[k] && i[k] < bi[k]))) {
+                    best[k] = v[k];
+                    bi[k] = i[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pooled[b * ldp + c + k] = best[k];
+        *reinterpret_cast<int4*>(argmax + b * C + c) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 segmax_bwd_kernel(const float* __restrict__ gp, int64_t ldg, const int* __restrict__ argmax,
                   float* __restrict__ G, int64_t ldG, int64_t rows, int L, int C) {
@@ -285,8 +344,18 @@ int spg_segmax_fwd(const float* Y, int64_t ldy, const float* scale, const float*
     if (B > 65535ll * 32768) return SPG_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t max_by = 65535;
+    const bool vec = (C & 3) == 0 && (ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0 &&
+                     ((uintptr_t)argmax & 15) == 0;
     for (int64_t b0 = 0; b0 < B; b0 += max_by) {
         const int64_t nb = min(max_by, B - b0);
+        if (vec) {
+            dim3 grid((unsigned)ceil_div64(C, 128), (unsigned)nb);
+            SPG_LAUNCH(K_SEGMAX_FWD, s, segmax_fwd_v4_kernel, grid, 256, 0, Y + b0 * L * ldy, ldy,
+                       scale, shift, relu, pooled + b0 * ldp, ldp, argmax + b0 * C, L, C);
+            int rcv = launch_status();
+            if (rcv) return rcv;
+            continue;
+        }
         dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)nb);
         SPG_LAUNCH(K_SEGMAX_FWD, s, segmax_fwd_kernel, grid, 256, 0, Y + b0 * L * ldy, ldy, scale,
                    shift, relu, pooled + b0 * ldp, ldp, argmax + b0 * C, L, C);

@@ -271,10 +271,12 @@ def test_batch_stats_and_bn_backward(dev, M, C):
     close(dY, Yr.grad, 1e-4, 1e-6)
 
 
-def test_segmax_and_cloud_rows(dev):
+@pytest.mark.parametrize("L,C", [(128, 70), (128, 64), (128, 256), (20, 132), (7, 8)])
+def test_segmax_and_cloud_rows(dev, L, C):
+    """C = 70: scalar pooling kernel; C % 4 == 0: the 128-bit one (incl. L < 8 row lanes)."""
     from superpoint_graph_b200 import ops
     torch.manual_seed(5)
-    B, F, L, C = 37, 14, 128, 70
+    B, F = 37, 14
     clouds = torch.randn(B, F, L, device=dev)
     T = torch.randn(B, 2, 2, device=dev)
     rows = ops.cloud_rows(clouds, T.reshape(B, 4), 16, add_eye=True)
