@@ -21,6 +21,12 @@ def test_reference_arm_json_line():
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert line["config"]["superpoints"] == 96
+    assert line["config"]["workload"].startswith("configs[1]")  # same workload string as the b200 arm
+    r, c = line["rates"], line["config"]
+    assert abs(r["points_per_s"] + r["edges_per_s"] - line["value"]) <= 1e-6 * line["value"]
+    assert abs(r["edge_iterations_per_s"] - 10 * r["edges_per_s"]) <= 1e-9 * r["edge_iterations_per_s"]
+    assert abs(r["superpoints_per_s"] * c["points"] - r["points_per_s"] * c["superpoints"]) \
+        <= 1e-6 * r["points_per_s"] * c["superpoints"]
 
 
 def test_b200_arm_fails_loudly_without_gpu():
