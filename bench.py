@@ -1,19 +1,30 @@
 #!/usr/bin/env python
-"""SPG train-step benchmark (BASELINE.json: "SPG train-step edges+points/sec ...; ECC scatter HBM %peak").
+"""SPG step benchmark (BASELINE.json: "SPG train-step edges+points/sec ...; ECC scatter HBM %peak").
 
-    python bench.py --gpus N --steps K --warmup W          # this repo's sm_100a path
-    python bench.py --impl reference --steps K --warmup W   # the reference's CPU algorithm (oracle port)
+    python bench.py --gpus N --steps K --warmup W                 # this repo's sm_100a path, configs[1]
+    python bench.py --impl reference --steps K --warmup W         # the reference's own CPU modules
+    python bench.py --workload room_fwd|sema3d_eval|vkitti_train|sweep_vv|sweep_mat [--nodes N]
 
-A "step" is one full training step of configs[1] ("S3DIS Area-5 fold training, gru_10_1_1_1_0,
-fp32") on one synthetic S3DIS-shaped batch per GPU: PointNet embedding of every superpoint that has
-a cloud, filter network, 10 x {ECC, GRUCellEx}, classifier, weighted CE, full backward,
-element-wise gradient clamp, Adam (learning/main.py:199-213).  value = (edges + points) per second
-summed over ranks (weak scaling: one batch of scenes per rank, one NCCL all-reduce of the flat
-gradient per step).
+Default workload (the headline line): one full training step of configs[1] ("S3DIS Area-5 fold
+training, gru_10_1_1_1_0, fp32") on one synthetic S3DIS-shaped batch per GPU: PointNet embedding of
+every superpoint that has a cloud, filter network, 10 x {ECC, GRUCellEx}, classifier, weighted CE,
+full backward, element-wise gradient clamp, Adam (learning/main.py:199-213).  value = (edges +
+points) per second summed over ranks (weak scaling: one batch of scenes per rank, one all-reduce of
+the flat gradient per step).  The other BASELINE configs are `--workload` lines (superpoint_graph_
+b200/workloads.py); inference workloads time main.py:229-264's forward.
+
+The line also carries `parity_rel_err`: the first step from the initial state, checked against one
+step of the CPU arm on the same batch (the bench measures, the tests assert).
 
 Timing: every step is bracketed by CUDA events on the launching stream; an L2 flush (a 256 MiB
 memset) runs between steps outside the brackets; the reported time is the max over ranks of the
 summed step times, after a barrier + synchronize on both sides of the K steps.
+
+Reference arm: baseline/_ref/ holds a verbatim copy of the reference's learning/{pointnet,graphnet,
+modules}.py and learning/ecc/* (baseline/install_ref.py, run by __graft_entry__.build() where
+/root/reference exists; git-ignored, shipped with the snapshot).  `--impl reference` drives those
+modules through their own API on the host CPU (baseline/ref_arm.py); `cpu_baseline.kind` is
+"reference" then, "port" (oracle/nets_ref) only if the copy is missing.
 """
 import argparse
 import json
@@ -30,10 +41,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "spg_train_step_edges_plus_points_per_sec"
+METRIC_EVAL = "spg_forward_edges_plus_points_per_sec"
 UNIT = "edges+points/s"
-PCFG = dict(n_conv=5, n_fc=3, n_conv_stn=3, n_fc_stn=2, nfeat_stn=14)
-MCFG = dict(fnet_widths=[13, 32, 128, 64, 32], bnidx=2, nrepeats=10, layernorm=True, ingate=True,
-            cat_all=False)
 
 
 def parse():
@@ -42,7 +51,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nodes", type=int, default=1024, help="superpoints per batch (2 scenes x 512)")
+    ap.add_argument("--workload", default="s3dis_train",
+                    help="s3dis_train (configs[1], default) | room_fwd (configs[0]) | sema3d_eval (configs[2]) | "
+                         "vkitti_train (configs[3]) | sweep_vv | sweep_mat (configs[4])")
+    ap.add_argument("--nodes", type=int, default=None, help="superpoints per batch (default: the workload's)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the one-step check against the reference/oracle")
     ap.add_argument("--ecc-nodes", type=int, default=100000, help="ECC roofline microbench size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -162,48 +175,144 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------ reference arm
+def host_info():
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count() or 1, "cpu_model": model}
+
+
+class CpuArm(object):
+    """The reference's CPU path for one workload: the reference's OWN modules when baseline/_ref is
+    installed (kind "reference": baseline/ref_arm.py), else the oracle port (kind "port")."""
+
+    def __init__(self, w, sd_ecc=None, sd_ptn=None):
+        from baseline import ref_arm
+        self.w, self.margs = w, w["margs"]
+        self.kind = "reference" if ref_arm.available() else "port"
+        self.sd = (sd_ecc, sd_ptn)
+        self._make()
+
+    def _make(self):
+        sd_ecc, sd_ptn = self.sd
+        if self.kind == "reference":
+            from baseline import ref_arm
+            self.impl = ref_arm.ReferenceStep(self.margs, seed=1)
+            if sd_ecc is not None:
+                self.impl.load(sd_ecc, sd_ptn)
+        else:
+            from oracle import nets_ref
+            from superpoint_graph_b200 import workloads
+            from superpoint_graph_b200.trainer import create_model
+            if sd_ecc is None:
+                torch.manual_seed(1)
+                model = create_model(self.margs)
+                sd_ecc, sd_ptn = model.ecc.state_dict(), model.ptn.state_dict()
+            self.pcfg, self.mcfg = workloads.oracle_cfg(self.margs)
+            self.impl = nets_ref.RefTrainer(sd_ptn, sd_ecc, self.pcfg, self.mcfg, lr=self.margs.lr,
+                                            grad_clip=self.margs.grad_clip, ecc_mode="loop")
+
+    def step(self, batch):
+        """-> (loss | None, logits)"""
+        if self.w["train"]:
+            return self.impl.train_step(batch) if self.kind == "reference" else self.impl.step(batch)
+        if self.kind == "reference":
+            return None, self.impl.eval_step(batch)
+        from oracle import nets_ref
+        with torch.no_grad():
+            return None, nets_ref.spg_forward(batch, self.impl.sd_ptn, self.impl.sd_ecc, self.pcfg, self.mcfg,
+                                              False, ecc_mode="loop")
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("the reference's own modules (baseline/_ref: learning/pointnet.py, graphnet.py, modules.py, "
+                    "ecc/*; use_pyg=0, cuda=False) through CloudEmbedder.run / GraphNetwork / cross_entropy / "
+                    "clamp / Adam")
+        return "oracle port of the reference CPU path (oracle/nets_ref, ecc_mode=loop)"
+
+    def pick_threads(self, batch, budget_s=20.0):
+        """torch's CPU kernels on these tensors get slower with very many threads; use the fastest of
+        a few thread counts up to all cores (one probe step each, bounded)."""
+        ncpu = os.cpu_count() or 1
+        best, best_t = ncpu, float("inf")
+        t_begin = time.perf_counter()
+        for th in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), ncpu}):
+            torch.set_num_threads(th)
+            self.step(batch)
+            t0 = time.perf_counter()
+            self.step(batch)
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = th, dt
+            if time.perf_counter() - t_begin > budget_s:
+                break
+        torch.set_num_threads(best)
+        self._make()  # probing advanced the optimizer: start again from the initial state
+        return best
+
+
+def config_of(w, counts, world):
+    """The `config` object — identical in both arms for the same launch."""
+    return dict(workload=w["title"],
+                parallelism="scene-parallel dp%d, one all-reduce of the flat gradient per step" % world
+                if w["train"] else "scene-parallel dp%d (inference: no collective)" % world,
+                l2="256 MiB memset between timed steps (outside the event brackets); 4 rotating batches",
+                **counts)
+
+
+def cpu_sample_nodes(w):
+    """Bounded CPU sample: the per-node Python loops of the reference make a CPU step ~1 ms per
+    superpoint-iteration; cap the sample so a K-step run ends within minutes."""
+    return min(w["nodes"], 2048)
+
+
 def run_reference(args):
-    """The reference's CPU algorithm (oracle port of learning/main.py:199-213 with the per-node
-    Python loops of GraphConvModule.py:82-88,114-121) on this box's host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the workload's step on this box's
+    host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import nets_ref
-    from superpoint_graph_b200.synthetic import make_batch
-    from superpoint_graph_b200.trainer import create_model, make_args
-
-    batch = make_batch(n_nodes=args.nodes, seed=1)
+    from superpoint_graph_b200 import workloads
+    w = workloads.get(args.workload, args.nodes)
+    counts_full = workload_counts(workloads.batch(w, 1)) if w["nodes"] <= 32768 else None
+    ws = workloads.get(args.workload, cpu_sample_nodes(w))
+    batch = workloads.batch(ws, 1)
     counts = workload_counts(batch)
-    margs = make_args()
-    model = create_model(margs)
-    sd_ecc = {k: v.clone() for k, v in model.ecc.state_dict().items()}
-    sd_ptn = {k: v.clone() for k, v in model.ptn.state_dict().items()}
-    threads = pick_cpu_threads(batch, margs, sd_ptn, sd_ecc)
-    tr = nets_ref.RefTrainer(sd_ptn, sd_ecc, PCFG, MCFG, lr=margs.lr, grad_clip=margs.grad_clip, ecc_mode="loop")
+    arm = CpuArm(ws)
+    threads = arm.pick_threads(batch)
     for _ in range(args.warmup):
-        tr.step(batch)
+        arm.step(batch)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        tr.step(batch)
+        arm.step(batch)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = (counts["edges"] + counts["points"]) / dt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = "%d full %s steps on a batch of %d superpoints (%s)" % (
+        args.steps, "training" if w["train"] else "inference", counts["superpoints"], arm.describe())
+    if ws["nodes"] != w["nodes"]:
+        sample += "; bounded sample of the %d-superpoint workload, throughput is size-normalised" % w["nodes"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload=workload_name(args.nodes), **counts),
+        "impl": "reference", "metric": METRIC if w["train"] else METRIC_EVAL, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": config_of(w, counts_full or workload_counts_nominal(w, counts), world),
         "rates": rates(counts, 1, dt * 1e3),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d full training steps of the same batch (oracle/nets_ref.RefTrainer, "
-                                   "ecc_mode=loop)" % args.steps},
+        "cpu_baseline": dict(value=value, unit=UNIT, cores=threads, kind=arm.kind, sample=sample, **host_info()),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_name(nodes):
-    return ("configs[1]: S3DIS-shaped training step, gru_10_1_1_1_0,f_13, fp32, "
-            "2 scenes x %d superpoints per GPU" % (nodes // 2))
+def workload_counts_nominal(w, sample_counts):
+    """Counts of the full workload when only a bounded sample was generated on the CPU arm (scaled)."""
+    k = w["nodes"] / float(sample_counts["superpoints"])
+    return {key: int(round(v * k)) for key, v in sample_counts.items()}
 
 
 def rates(counts, world, ms_per_step):
@@ -214,46 +323,40 @@ def rates(counts, world, ms_per_step):
 
 
 # ------------------------------------------------------------------------------------ our arm
-def pick_cpu_threads(batch, margs, sd_ptn, sd_ecc):
-    """torch's CPU kernels on these small tensors get slower with very many threads; the baseline
-    uses the fastest of a few thread counts (one probe step each), not blindly all cores."""
-    from oracle import nets_ref
-    ncpu = os.cpu_count() or 1
-    best, best_t = 1, float("inf")
-    for th in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), ncpu}):
-        torch.set_num_threads(th)
-        tr = nets_ref.RefTrainer(sd_ptn, sd_ecc, PCFG, MCFG, lr=margs.lr, grad_clip=margs.grad_clip, ecc_mode="loop")
-        tr.step(batch)
+def cpu_baseline(w, sd_ecc, sd_ptn, budget_s=25.0):
+    """`cpu_baseline` of the b200 line: the same CPU arm, bounded sample, timed on this box."""
+    from superpoint_graph_b200 import workloads
+    ws = workloads.get(w["name"], cpu_sample_nodes(w))
+    batch = workloads.batch(ws, 1)
+    counts = workload_counts(batch)
+    arm = CpuArm(ws, sd_ecc, sd_ptn)
+    threads = arm.pick_threads(batch, budget_s=budget_s / 2)
+    arm.step(batch)  # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 5 and (time.perf_counter() - t_start) < budget_s / 2:
         t0 = time.perf_counter()
-        tr.step(batch)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = th, dt
-    torch.set_num_threads(best)
-    return best
+        arm.step(batch)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]
+    return dict(value=(counts["edges"] + counts["points"]) / dt, unit=UNIT, cores=threads, kind=arm.kind,
+                sample="median of %d full steps on a batch of %d superpoints on the host (%s)" % (
+                    len(times), counts["superpoints"], arm.describe()),
+                ms_per_step=dt * 1e3, **host_info())
 
 
-def cpu_baseline(batch, counts, margs, sd_ptn, sd_ecc, budget_s=25.0):
-    from oracle import nets_ref
-    threads = pick_cpu_threads(batch, margs, sd_ptn, sd_ecc)
-    out = {}
-    for mode in ("loop", "vec"):
-        tr = nets_ref.RefTrainer(sd_ptn, sd_ecc, PCFG, MCFG, lr=margs.lr, grad_clip=margs.grad_clip, ecc_mode=mode)
-        tr.step(batch)  # warm-up
-        times = []
-        t_start = time.perf_counter()
-        while len(times) < 5 and (time.perf_counter() - t_start) < budget_s / 2:
-            t0 = time.perf_counter()
-            tr.step(batch)
-            times.append(time.perf_counter() - t0)
-        times.sort()
-        out[mode] = (times[len(times) // 2], len(times))
-    dt, n = out["loop"]
-    return {"value": (counts["edges"] + counts["points"]) / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "median of %d full training steps of the same batch on the host (oracle port of the "
-                      "reference CPU path incl. its per-node Python loops)" % n,
-            "ms_per_step": dt * 1e3,
-            "vectorized_ms_per_step": out["vec"][0] * 1e3}
+def parity_check(w, batch, sd_ecc, sd_ptn, loss, logits):
+    """One step of the CPU arm from the same initial state on the same batch: relative errors of the
+    GPU step's loss and logits (the bench asserts nothing; the line carries the numbers)."""
+    arm = CpuArm(w, sd_ecc, sd_ptn)
+    ref_loss, ref_logits = arm.step(batch)
+    lg = logits.detach().float().cpu()
+    out = {"logits": float((lg - ref_logits).abs().max() / ref_logits.abs().max()), "checker": arm.kind,
+           "superpoints": int(lg.shape[0])}
+    if ref_loss is not None:
+        out["loss"] = abs(float(loss) - ref_loss) / abs(ref_loss)
+    return out
 
 
 def ncu_traffic():
@@ -364,9 +467,8 @@ def loader_roofline(dev, pk, with_cpu):
 def run_b200(args):
     import torch.distributed as dist
 
-    from superpoint_graph_b200 import _lib, ops
-    from superpoint_graph_b200.synthetic import make_batch
-    from superpoint_graph_b200.trainer import HostBatch, Trainer, create_model, make_args
+    from superpoint_graph_b200 import _lib, ops, workloads
+    from superpoint_graph_b200.trainer import HostBatch, Trainer, create_model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -382,16 +484,18 @@ def run_b200(args):
         pg = dist.group.WORLD
     pk = peaks()
 
-    margs = make_args()
+    w = workloads.get(args.workload, args.nodes)
+    margs, train = w["margs"], w["train"]
     torch.manual_seed(1)  # --seed 1 (main.py:77); Trainer also broadcasts rank 0's parameters once
     model = create_model(margs)
     sd_ecc = {k: v.clone() for k, v in model.ecc.state_dict().items()}
     sd_ptn = {k: v.clone() for k, v in model.ptn.state_dict().items()}
     model.to(dev)
-    trainer = Trainer(model, margs, process_group=pg, world_size=world)
+    trainer = Trainer(model, margs, process_group=pg, world_size=world, dtype=w["dtype"])
 
     # 4 distinct batches per rank, rotated; rank-offset seeds (scene-parallel)
-    batches = [make_batch(n_nodes=args.nodes, seed=1 + 1000 * rank + i) for i in range(4)]
+    nb = 4 if w["nodes"] <= 20000 else 2
+    batches = [workloads.batch(w, 1 + 1000 * rank + i) for i in range(nb)]
     hbs = [HostBatch(b) for b in batches]
     counts = workload_counts(batches[0])
     units = [workload_counts(b)["edges"] + workload_counts(b)["points"] for b in batches]
@@ -399,14 +503,30 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
+    def step(db):
+        if train:
+            return trainer.train_step(db)
+        return None, trainer.eval_step(db)
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- self-check: the very first step from the initial state against the CPU arm (rank 0)
+    parity = None
+    loss0, logits0 = step(dbs[0])
+    torch.cuda.synchronize()
+    if rank == 0 and not args.no_parity:
+        if w["nodes"] <= 4096:
+            parity = parity_check(w, batches[0], sd_ecc, sd_ptn, None if loss0 is None else float(loss0[0]), logits0)
+        else:
+            parity = {"skipped": "CPU step at %d superpoints exceeds the bench's time bound; this shape is "
+                                 "covered by tests/test_gpu_shapes.py" % w["nodes"]}
+
     # ---- device-resident timing (value)
     for i in range(args.warmup):
-        trainer.train_step(dbs[i % 4])
+        step(dbs[i % nb])
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -418,10 +538,10 @@ def run_b200(args):
         flush.zero_()  # L2 flush, outside the event bracket
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        trainer.train_step(dbs[i % 4])
+        step(dbs[i % nb])
         e.record()
         evs.append((s, e))
-        done_units += units[i % 4]
+        done_units += units[i % nb]
     barrier()
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
@@ -437,15 +557,15 @@ def run_b200(args):
 
     eager_ms, eager_value = total_ms / args.steps, value
     # ---- same K steps replayed from CUDA graphs (one per distinct batch shape): identical kernels,
-    # one graph launch per step instead of ~200 kernel launches
+    # one graph launch per step instead of ~100 kernel launches
     graph_keys, graph_err = None, None
-    if not args.no_graph:
+    if not args.no_graph and train:
         try:
             per_step0 = ops.total_launches()
-            graph_keys = [trainer.capture(dbs[i], key=i, warmup=1) for i in range(4)]
-            launches_per_step = (ops.total_launches() - per_step0) // 8 + 1  # (1 warm-up + 1 capture) x 4
+            graph_keys = [trainer.capture(dbs[i], key=i, warmup=1) for i in range(nb)]
+            launches_per_step = (ops.total_launches() - per_step0) // (2 * nb) + 1  # (1 warm-up + 1 capture) x nb
             for i in range(args.warmup):
-                trainer.replay(graph_keys[i % 4])
+                trainer.replay(graph_keys[i % nb])
             barrier()
             sampler = ClockSampler(local)
             sampler.start()
@@ -455,10 +575,10 @@ def run_b200(args):
                 flush.zero_()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                trainer.replay(graph_keys[i % 4])
+                trainer.replay(graph_keys[i % nb])
                 e.record()
                 evs.append((s, e))
-                done_units += units[i % 4]
+                done_units += units[i % nb]
             barrier()
             wall = time.perf_counter() - t_wall
             clocks = sampler.stop()
@@ -476,13 +596,14 @@ def run_b200(args):
 
     # ---- end-to-end through the public API with host buffers (H2D + step + D2H of loss/logits)
     h2d = hbs[0].h2d_bytes()
-    out_host = torch.empty((args.nodes, margs.classes), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((w["nodes"], margs.classes), dtype=torch.float32).pin_memory()
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
     def e2e_step(i):
         if graph_keys is not None:  # refresh the graph's static input buffers, then replay
-            hbs[i % 4].copy_into(dbs[i % 4])
-            return trainer.replay(graph_keys[i % 4])
-        return trainer.train_step(hbs[i % 4].to_device(dev))
+            hbs[i % nb].copy_into(dbs[i % nb])
+            return trainer.replay(graph_keys[i % nb])
+        return step(hbs[i % nb].to_device(dev))
 
     for i in range(0 if args.no_e2e else max(3, args.warmup // 2)):
         e2e_step(i)
@@ -494,11 +615,12 @@ def run_b200(args):
         s.record()
         loss, logits = e2e_step(i)
         out_host[:logits.shape[0]].copy_(logits, non_blocking=True)
-        loss_host.copy_(loss, non_blocking=True)
+        if loss is not None:
+            loss_host.copy_(loss, non_blocking=True)
         e.record()
         e.synchronize()  # the trainer reads loss/logits on the host every step (main.py:216-221)
         e2e_ms += s.elapsed_time(e)
-        e2e_units += units[i % 4]
+        e2e_units += units[i % nb]
     barrier()
     t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     u2 = torch.tensor([float(e2e_units)], dtype=torch.float64, device=dev)
@@ -506,16 +628,13 @@ def run_b200(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         dist.all_reduce(u2, op=dist.ReduceOp.SUM)
     e2e_value = float(u2) / (float(t2) * 1e-3)
-    d2h = int(args.nodes * margs.classes * 4 + 4)
+    d2h = int(w["nodes"] * margs.classes * 4 + (4 if train else 0))
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload=workload_name(args.nodes),
-                       parallelism="scene-parallel dp%d, one NCCL all-reduce of the flat gradient per step" % world,
-                       l2="256 MiB memset between timed steps (outside the event brackets); 4 rotating batches",
-                       **counts),
+        "metric": METRIC if train else METRIC_EVAL, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": config_of(w, counts, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(t2) / args.steps},
         "rates": rates(counts, world, total_ms / args.steps),
@@ -526,6 +645,8 @@ def run_b200(args):
         "clocks": clocks,
         "peaks": pk["source"],
     }
+    if parity is not None:
+        line["parity_rel_err"] = parity
 
     if graph_err:
         line["cuda_graph_error"] = graph_err
@@ -537,7 +658,7 @@ def run_b200(args):
                   "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0]}
         nprof = 3
         for i in range(nprof):
-            trainer.train_step(dbs[i % 4]) if world == 1 else None
+            step(dbs[i % nb]) if world == 1 else None
         torch.cuda.synchronize()
         ops.prof_enable(0)
         if world == 1:
@@ -569,7 +690,10 @@ def run_b200(args):
             if gname in dense:
                 line["roofline"] = dense[gname]
             line["roofline_dense_kernels"] = dense
+        extras = args.workload == "s3dis_train"  # the component rooflines ride on the headline line only
         try:
+            if not extras:
+                raise StopIteration
             er = ecc_roofline(dev, args.ecc_nodes, pk)
             line["roofline_ecc"] = er
             k = er["kernels"]["mat_fwd"]
@@ -585,16 +709,22 @@ def run_b200(args):
                 line["roofline"] = ecc_obj
             else:
                 line["roofline_ecc_scatter"] = ecc_obj
+        except StopIteration:
+            pass
         except Exception as ex:  # keep the bench line even if the microbench cannot run
             line["roofline_ecc_error"] = repr(ex)
         try:
+            if not extras:
+                raise StopIteration
             line["roofline_loader"] = loader_roofline(dev, pk, not args.no_cpu_baseline)
+        except StopIteration:
+            pass
         except Exception as ex:
             line["roofline_loader_error"] = repr(ex)
 
     if rank == 0 and world == 1 and args.trace_gemm:
         ops.GEMM_TRACE = []
-        trainer.train_step(dbs[0])
+        step(dbs[0])
         torch.cuda.synchronize()
         agg = {}
         for desc, e0, e1 in ops.GEMM_TRACE:
@@ -605,7 +735,7 @@ def run_b200(args):
         for desc, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
             print("[gemm_f32] %-40s x%d  %.3f ms" % (desc, n, ms), file=sys.stderr)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(batches[0], counts, margs, sd_ptn, sd_ecc)
+        line["cpu_baseline"] = cpu_baseline(w, sd_ecc, sd_ptn)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -664,7 +664,8 @@ int spg_gru_bwd(const float* x, const float* h, const float* grad_hy, const floa
 }
 
 int spg_rnn_vv_supported(int64_t n_nodes, int hidden) {
-    return hidden == kRecH && n_nodes > 0 && gru_rows_per_warp(n_nodes) == 1;
+    // any number of nodes: the kernels walk the nodes grid-strided inside every step
+    return hidden == kRecH && n_nodes > 0 && n_nodes < ((int64_t)1 << 31) / (4 * kRecH);
 }
 
 int spg_rnn_vv_fwd(float* hs, float* inps, const float* w, const int32_t* tgt_rowptr,
@@ -687,10 +688,19 @@ int spg_rnn_vv_fwd(float* hs, float* inps, const float* w, const int32_t* tgt_ro
     if (blocks <= 0) return SPG_E_UNSUPPORTED;
     e = cudaMemsetAsync(barrier_ws, 0, sizeof(unsigned), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
-    SPG_LAUNCH(K_RNN_FWD, (cudaStream_t)stream, rnn_vv_fwd_kernel, (unsigned)blocks,
-               kGruWarps * 32, smem, hs, inps, reinterpret_cast<const float4*>(w), tgt_rowptr, idxn,
-               weight_ih, weight_hh, bias_ih, bias_hh, ig_weight, ig_bias, (int)n_nodes, n_repeats,
-               flags, reinterpret_cast<unsigned*>(barrier_ws));
+    // cooperative launch: the driver guarantees that all CTAs are co-resident (the grid barrier
+    // spins on them) or fails the launch; other streams' kernels cannot starve the grid
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    int n_i = (int)n_nodes;
+    unsigned* bar = reinterpret_cast<unsigned*>(barrier_ws);
+    void* kargs[] = {&hs, &inps, &w4, &tgt_rowptr, &idxn, &weight_ih, &weight_hh, &bias_ih, &bias_hh,
+                     &ig_weight, &ig_bias, &n_i, &n_repeats, &flags, &bar};
+    {
+        ::spg::LaunchScope _scope(K_RNN_FWD, (cudaStream_t)stream);
+        e = cudaLaunchCooperativeKernel((const void*)rnn_vv_fwd_kernel, dim3((unsigned)blocks),
+                                        dim3(kGruWarps * 32), kargs, smem, (cudaStream_t)stream);
+    }
+    if (e != cudaSuccess) return (int)e;
     return launch_status();
 }
 
@@ -719,11 +729,19 @@ int spg_rnn_vv_bwd(const float* hs, const float* inps, const float* w, const flo
     if (blocks <= 0) return SPG_E_UNSUPPORTED;
     e = cudaMemsetAsync(barrier_ws, 0, sizeof(unsigned), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
-    SPG_LAUNCH(K_RNN_BWD, (cudaStream_t)stream, rnn_vv_bwd_kernel, (unsigned)blocks,
-               kGruWarps * 32, smem, hs, inps, reinterpret_cast<const float4*>(w), grad_top,
-               grad_cat, tgt_rowptr, src_rowptr, src_perm, edge_tgt, weight_ih, weight_hh, bias_ih,
-               bias_hh, ig_weight, ig_bias, grad_inp, d_h_ws, grad_h0, d_gi, d_gh, d_q, xprime,
-               dpre, (int)n_nodes, n_repeats, flags, reinterpret_cast<unsigned*>(barrier_ws));
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    int n_i = (int)n_nodes;
+    unsigned* bar = reinterpret_cast<unsigned*>(barrier_ws);
+    void* kargs[] = {&hs, &inps, &w4, &grad_top, &grad_cat, &tgt_rowptr, &src_rowptr, &src_perm,
+                     &edge_tgt, &weight_ih, &weight_hh, &bias_ih, &bias_hh, &ig_weight, &ig_bias,
+                     &grad_inp, &d_h_ws, &grad_h0, &d_gi, &d_gh, &d_q, &xprime, &dpre, &n_i,
+                     &n_repeats, &flags, &bar};
+    {
+        ::spg::LaunchScope _scope(K_RNN_BWD, (cudaStream_t)stream);
+        e = cudaLaunchCooperativeKernel((const void*)rnn_vv_bwd_kernel, dim3((unsigned)blocks),
+                                        dim3(kGruWarps * 32), kargs, smem, (cudaStream_t)stream);
+    }
+    if (e != cudaSuccess) return (int)e;
     return launch_status();
 }
 

@@ -48,8 +48,10 @@ __global__ void ce_loss_final_kernel(const double* __restrict__ acc, float* __re
                                      float* __restrict__ dlogits, int64_t total) {
     const double wsum = acc[1];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) loss[0] = (float)(acc[0] / wsum);
-    if (dlogits && i < total) dlogits[i] = (float)((double)dlogits[i] / wsum);
+    if (i == 0) loss[0] = (float)(acc[0] / wsum);  // 0/0 = NaN for an all-ignored batch, as torch
+    // an all-ignored batch (wsum == 0) has a NaN loss but ZERO gradients in torch's cross_entropy:
+    // every d_logits row was written as 0 by the first kernel, leave it
+    if (dlogits && i < total && wsum != 0.0) dlogits[i] = (float)((double)dlogits[i] / wsum);
 }
 
 __global__ void __launch_bounds__(256)
@@ -59,7 +61,8 @@ clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
-        if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+        // p.grad.clamp_ propagates NaN (fminf/fmaxf would turn it into -clip and hide a divergence)
+        if (clip > 0.f && gi == gi) gi = fminf(fmaxf(gi, -clip), clip);
         const float pi = p[i];
         if (wd != 0.f) gi = fmaf(wd, pi, gi);
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -83,7 +86,8 @@ clamp_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
-        if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+        // p.grad.clamp_ propagates NaN (fminf/fmaxf would turn it into -clip and hide a divergence)
+        if (clip > 0.f && gi == gi) gi = fminf(fmaxf(gi, -clip), clip);
         const float pi = p[i];
         if (wd != 0.f) gi = fmaf(wd, pi, gi);
         const float mi = b1 * m[i] + (1.f - b1) * gi;

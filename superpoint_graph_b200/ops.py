@@ -36,14 +36,22 @@ def _c(t):
 
 
 _workspaces = {}
+_retired_workspaces = []  # outgrown buffers are never freed: a captured CUDA graph may hold their address
 
 
-def workspace(nfloats, device):
-    """Per (device, stream) scratch buffer; stream order makes reuse across calls safe."""
-    key = (device.index, _lib.current_stream())
+def workspace(nfloats, device, slot=0):
+    """Per (device, stream, slot) scratch buffer; stream order makes reuse across calls safe.
+    Slots keep buffers that are live in the SAME kernel apart (0: split-K / partial products,
+    1: statistics partials).  A buffer that has to grow is replaced by one at least twice as large
+    and the old one is kept alive for the life of the process (Trainer.capture bakes workspace
+    addresses into CUDA graphs; geometric growth bounds the retired total by the final size)."""
+    key = (device.index, _lib.current_stream(), slot)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nfloats:
-        buf = torch.empty(max(int(nfloats), 1 << 16), dtype=torch.float32, device=device)
+        grow = 0 if buf is None else 2 * buf.numel()
+        if buf is not None:
+            _retired_workspaces.append(buf)
+        buf = torch.empty(max(int(nfloats), grow, 1 << 16), dtype=torch.float32, device=device)
         _workspaces[key] = buf
     return buf
 
@@ -280,7 +288,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
         split_k = 1 if stats else _auto_split(M, N, K)
     ws = workspace(split_k * M * N, dev) if split_k > 1 else None
     tiles = (M + 127) // 128
-    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev) if stats else None
+    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev, slot=1) if stats else None
     _lib.call("spg_gemm", A, lda, int(a_kmajor), B, ldb, int(b_kmajor), bias, out, ldc, M, N, K,
               a_s, a_t, int(bool(a_r)), b_s, b_t, int(bool(b_r)), split_k, ws, sws,
               _lib.current_stream())
@@ -351,7 +359,7 @@ def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=Fal
     out = torch.empty((M, N), dtype=torch.float32, device=dev)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
     tiles = int(_lib.lib().spg_tc_gemm_stats_partials(int(M), int(N), int(K)))
-    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev) if stats else None
+    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev, slot=1) if stats else None
     GEMM_FLOPS[0] += 2 * M * N * K
     TC_FLOPS[0] += 2 * M * N * K
     _lib.call("spg_tc_gemm", A, lda, img, bias, out, N, M, N, K, a_s, a_t, int(bool(a_r)), sws,

@@ -86,7 +86,8 @@ class GraphNetwork(nn.Module):
         """Hands the batch's graph structure to every convolution module (i-th info -> i-th conv)."""
         if not isinstance(gc_infos, (list, tuple)):
             gc_infos = [gc_infos]
-        for gconv, info in zip(self.gconvs, gc_infos):
+        for i, gconv in enumerate(self.gconvs):
+            info = gc_infos[i]  # IndexError when fewer infos than convolutions, as graphnet.py:91-93
             if cuda:
                 info.cuda()
             gconv.set_info(info)

@@ -315,21 +315,30 @@ class CloudEmbedder():
 
     def run_full(self, model, clouds_meta, clouds_flag, clouds, clouds_global):
         clouds, clouds_global, idx_valid = self._prep(clouds_flag, clouds, clouds_global)
-        out = model.ptn(clouds, clouds_global)
-        return _ScatterRows.apply(out, idx_valid, clouds_flag.size(0))
+        return self._embed_full(model, clouds, clouds_global, idx_valid, clouds_flag.size(0))
 
     def run_full_monger(self, model, clouds_meta, clouds_flag, clouds, clouds_global):
-        """Memory mongering (ref: learning/pointnet.py:160-180): forward without saving, full
-        recomputation in `bw_hook`."""
         clouds, clouds_global, idx_valid = self._prep(clouds_flag, clouds, clouds_global)
+        return self._embed_monger(model, clouds, clouds_global, idx_valid, clouds_flag.size(0))
+
+    def run_resident(self, model, clouds, clouds_global, idx_valid, n_rows):
+        """`run` for a batch that already lives on the device (Trainer / CUDA-graph path): same
+        embedding code as run_full / run_full_monger minus the H2D copies and the host-side
+        `nonzero` of the flags (done once when the batch was collated)."""
+        fn = self._embed_monger if self.args.ptn_mem_monger else self._embed_full
+        return fn(model, clouds, clouds_global, idx_valid, n_rows)
+
+    def _embed_full(self, model, clouds, clouds_global, idx_valid, n_rows):
+        out = model.ptn(clouds, clouds_global)
+        return _ScatterRows.apply(out, idx_valid, n_rows)
+
+    def _embed_monger(self, model, clouds, clouds_global, idx_valid, n_rows):
+        """Memory mongering (ref: learning/pointnet.py:160-180): forward without saving, full
+        recomputation in `bw_hook`.  As in the reference, a training step therefore runs the
+        training-mode forward twice and the BatchNorm running statistics see two updates."""
         was_training = model.training
         with torch.no_grad():
-            if was_training:
-                # batch statistics are needed but nothing is kept; running stats must only be
-                # updated once per step, which the recomputation in bw_hook does.
-                out = _forward_no_stat_update(model.ptn, clouds, clouds_global)
-            else:
-                out = model.ptn(clouds, clouds_global)
+            out = model.ptn(clouds, clouds_global)
         out = out.detach().requires_grad_(was_training)
 
         def bw_hook():
@@ -337,16 +346,7 @@ class CloudEmbedder():
             out_v2.backward(out.grad)
 
         self.bw_hook = bw_hook
-        return _ScatterRows.apply(out, idx_valid, clouds_flag.size(0))
-
-
-def _forward_no_stat_update(ptn, clouds, clouds_global):
-    """Training-mode forward whose BatchNorm running statistics are restored afterwards.
-
-    The reference's monger path updates running stats twice per step (no_grad forward +
-    recomputation, ref: learning/pointnet.py:166-174); to stay bit-compatible with that observable
-    behaviour we simply run the normal training forward, i.e. we also update twice."""
-    return ptn(clouds, clouds_global)
+        return _ScatterRows.apply(out, idx_valid, n_rows)
 
 
 class _ScatterRows(torch.autograd.Function):

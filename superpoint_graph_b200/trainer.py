@@ -118,8 +118,10 @@ class DeviceBatch(object):
 class Trainer(object):
     """zero_grad / forward / loss / backward / (all-reduce) / clamp / Adam, as one object."""
 
-    def __init__(self, model, args, class_weights=None, process_group=None, world_size=1):
-        self.model, self.args = model, args
+    def __init__(self, model, args, class_weights=None, process_group=None, world_size=1, dtype="f32"):
+        if dtype not in ("f32", "bf16"):
+            raise ValueError("dtype must be 'f32' or 'bf16'")
+        self.model, self.args, self.dtype = model, args, dtype
         self.flat, self.params = flatten_parameters(model)
         self.flat_grad = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
@@ -143,8 +145,8 @@ class Trainer(object):
             for gc in self.model.ecc.gconvs:
                 if hasattr(gc, "prefetch_filters"):
                     gc.prefetch_filters()
-        out = self.model.ptn(db.clouds, db.clouds_global)
-        emb = _scatter(out, db.idx_valid, db.n_nodes)
+        # CloudEmbedder.run's device-resident twin (same code path behind it, incl. mem-monger)
+        emb = self.embedder.run_resident(self.model, db.clouds, db.clouds_global, db.idx_valid, db.n_nodes)
         return self.model.ecc(emb)
 
     def compute_gradients(self, db):
@@ -182,12 +184,18 @@ class Trainer(object):
     def apply_update(self):
         """One all-reduce of the flat gradient (scene-parallel ranks), then clamp + Adam in one
         kernel (gradient averaged by 1/world before the clamp, as main.py:210-213 on one GPU)."""
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        self.reduce_gradients()
         self.step_count += 1
         ops.clamp_adam_dev_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
                             lr=self.args.lr, weight_decay=self.args.wd, grad_clip=self.args.grad_clip,
                             grad_scale=1.0 / self.world_size)
+
+    def reduce_gradients(self):
+        """The step's only collective: SUM of the flat gradient over the scene-parallel ranks (the
+        1/world average is applied inside the clamp+Adam kernel, before the clamp)."""
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        return self.flat_grad
 
     def train_step(self, db):
         """One optimisation step on a device-resident batch; returns (loss[1], logits)."""
@@ -200,11 +208,34 @@ class Trainer(object):
     # static given the shapes: one capture, then one graph launch per step instead of ~250 kernel
     # launches.  The collective and the optimizer kernel stay outside the graph (NCCL is not
     # captured).  Batches of new shapes simply run eagerly.
+    def _snapshot(self):
+        bufs = [b for b in self.model.buffers()]
+        return (self.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone(),
+                self.step_count, bufs, [b.clone() for b in bufs])
+
+    def _restore(self, snap):
+        flat, m, v, step_dev, step_count, bufs, saved = snap
+        self.flat.copy_(flat)
+        self.exp_avg.copy_(m)
+        self.exp_avg_sq.copy_(v)
+        self.step_dev.copy_(step_dev)
+        self.step_count = step_count
+        for b, sv in zip(bufs, saved):
+            b.copy_(sv)
+
     def capture(self, db, key=None, warmup=2):
-        """Captures compute_gradients on the static tensors of `db`; returns the key for replay()."""
+        """Captures compute_gradients on the static tensors of `db`; returns the key for replay().
+        Free of side effects: the `warmup` (>= 1) eager steps that prime workspaces, weight-image
+        tables and lazy handles run on a snapshot — parameters, Adam state, step count and BatchNorm
+        buffers are restored before the capture."""
+        if warmup < 1:
+            raise ValueError("capture() needs at least one warm-up step (the batched weight packing uploads "
+                             "its job table on first use, which cannot happen inside a capture)")
         key = key if key is not None else id(db)
+        snap = self._snapshot()
         for _ in range(warmup):
             self.train_step(db)
+        self._restore(snap)
         # the job table of the batched weight packing is uploaded on first use: do that outside
         # the capture (a pageable H2D copy cannot be captured)
         self._prepack(db)
@@ -231,8 +262,41 @@ class Trainer(object):
         self.model.eval()
         return self.forward(db)
 
+    # ---- optimizer state in torch.optim.Adam's layout (checkpoints of main.py:342-346,390-412)
+    def optimizer_state_dict(self):
+        """{'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} with one entry per
+        parameter in model.parameters() order — what torch.optim.Adam(model.parameters()).state_dict()
+        holds after the same number of steps."""
+        state, off = {}, 0
+        step = int(self.step_dev.item())
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            if step > 0:
+                state[i] = {"step": torch.tensor(float(step)),
+                            "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+            off += n
+        group = {"lr": self.args.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": self.args.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
 
-def _scatter(out, idx_valid, n_nodes):
-    from .spg_pointnet import _ScatterRows
+    def load_optimizer_state_dict(self, sd):
+        off, step = 0, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is None:
+                self.exp_avg[off:off + n].zero_()
+                self.exp_avg_sq[off:off + n].zero_()
+            else:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                step = max(step, int(float(st["step"])))
+            off += n
+        if sd.get("param_groups"):
+            self.args.lr = sd["param_groups"][0].get("lr", self.args.lr)
+        self.step_dev.fill_(step)
+        self.step_count = step
 
-    return _ScatterRows.apply(out, idx_valid, n_nodes)
+

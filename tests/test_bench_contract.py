@@ -1,4 +1,4 @@
-"""CPU: the reference arm of bench.py (oracle port on the host cores) prints one JSON line with the
+"""CPU: the reference arm of bench.py (the reference's own modules from baseline/_ref on the host cores) prints one JSON line with the
 contract's keys; the b200 arm refuses to run without a CUDA device (no CPU fallback)."""
 import json
 import os
@@ -18,7 +18,11 @@ def test_reference_arm_json_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
                 "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "learning", "pointnet.py"))
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["cpu_baseline"]["nproc"] >= line["cpu_baseline"]["cores"] >= 1
+    assert set(line["config"]) == {"workload", "parallelism", "l2", "superpoints", "embedded_superpoints",
+                                   "points", "edges"}
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert line["config"]["superpoints"] == 96
     assert line["config"]["workload"].startswith("configs[1]")  # same workload string as the b200 arm

@@ -26,12 +26,20 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from superpoint_graph_b200.synthetic import make_batch
-    from superpoint_graph_b200.trainer import create_model, flatten_parameters, make_args
+    from superpoint_graph_b200.trainer import Trainer, create_model, make_args
 
     torch.manual_seed(100 + rank)  # different ambient RNG state on every rank ...
     args = make_args(model_config="gru_2_1_1_1_0,f_13")
     model = create_model(args)  # ... yet identical replicas: ecc is built first, ptn reseeds to 0
-    flat, params = flatten_parameters(model)
+    # the Trainer itself (host logic only on CPU: flat buffers, broadcast, the gradient collective);
+    # world_size > 1 makes its constructor broadcast rank 0's parameters
+    ref_flat_before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    tr = Trainer(model, args, process_group=dist.group.WORLD, world_size=world)
+    flat, params = tr.flat, tr.params
+    bcast = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(bcast, flat)
+    same_after_bcast = all(torch.equal(bcast[0], g) for g in bcast)
+    flat.copy_(ref_flat_before)  # undo the broadcast for the replica checks below
     # (1) parameters are views of the flat buffer, in model.parameters() order
     assert flat.numel() == sum(p.numel() for p in params)
     off = 0
@@ -51,10 +59,10 @@ def _worker(rank, world, port, q):
     torch.manual_seed(7 + rank)
     for p in params:
         p.grad = torch.randn_like(p)
-    flat_grad = torch.empty_like(flat)
-    torch.cat([p.grad.reshape(-1) for p in params], out=flat_grad)
-    mine = flat_grad.clone()
-    dist.all_reduce(flat_grad)
+    torch.cat([p.grad.reshape(-1) for p in params], out=tr.flat_grad)  # what compute_gradients leaves
+    mine = tr.flat_grad.clone()
+    flat_grad = tr.reduce_gradients()  # Trainer's own collective (apply_update = this + clamp/Adam kernel)
+    assert flat_grad is tr.flat_grad
     others = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(others, mine)
     ok_sum = torch.allclose(flat_grad, sum(others), atol=1e-6)
@@ -62,7 +70,8 @@ def _worker(rank, world, port, q):
     ok_order = torch.all(avg_clamped.abs() <= 1)
     if rank == 0:
         q.put(dict(same_ptn=bool(same_ptn), same_all=bool(same_all), sigs=[float(s) for s in sigs],
-                   ok_sum=bool(ok_sum), ok_order=bool(ok_order), n=flat.numel()))
+                   ok_sum=bool(ok_sum), ok_order=bool(ok_order), n=flat.numel(),
+                   same_after_bcast=bool(same_after_bcast)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,6 +89,7 @@ def test_scene_parallel_plumbing_world2():
     res = q.get()
     assert res["same_ptn"], "PointNet replicas differ across ranks"
     assert res["ok_sum"] and res["ok_order"]
+    assert res["same_after_bcast"], "Trainer(world_size>1) must broadcast rank 0's parameters"
     assert res["sigs"][0] != res["sigs"][1], "ranks must train on different scenes"
     assert res["n"] == 188836 + 22925 - (13 * 32 + 13) + (13 * 32 + 13)
     # the ECC part is initialised from the ambient RNG (as in the reference, main.py:77 seeds it
