@@ -182,12 +182,12 @@ int spg_colstats_merge_fold(float* partials, int64_t n_partials, int C, float* m
 
 /* tcgen05 tensor-core path of the same product for the large point-wise layers:
  *   C[M,N] = f(A)[M,K] * B[N,K]^T + bias in fp32-equivalent precision (3xTF32 split, fp32 TMEM
- *   accumulation), N in {64,128,256}, K % 32 == 0, lda/ldc % 4 == 0, 16-byte aligned pointers.
+ *   accumulation), lda/ldc % 4 == 0, 16-byte aligned pointers.
  * B is given as a pre-split, pre-swizzled image built by spg_tc_pack_weights from W (ld = ldw):
  *   transpose=0: B[n][k] = W[n][k] (forward, W = [N,K]); transpose=1: B[n][k] = W[k][n]
  *   (data gradient, W = [K,N]).  image needs spg_tc_weight_image_floats(N,K) floats; entries with
  *   k >= k_valid are zero (K padded to a multiple of 32, e.g. the 14 input features -> 32).
- * stats_ws as in spg_gemm.  Returns SPG_E_UNSUPPORTED for other shapes (use spg_gemm).          */
+ * Returns SPG_E_UNSUPPORTED for other shapes (use spg_gemm).                                      */
 int64_t spg_tc_weight_image_floats(int N, int K);
 int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, int k_valid,
                         float* image, spg_stream_t stream);
@@ -195,13 +195,42 @@ int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K
  * {W, ldw, transpose, N, K, k_valid, image, first element index}; total = sum N*K.            */
 int spg_tc_pack_weights_multi(const int64_t* table, int n_jobs, int64_t total, spg_stream_t stream);
 int spg_tc_gemm_supported(int64_t M, int N, int K);
-/* kernel generation (1: one CTA per tile; 2, default: persistent warp-specialised, resident weights)
- * and the number of statistics partials per column spg_tc_gemm writes for a given problem.     */
-int spg_tc_set_generation(int gen);
-int64_t spg_tc_gemm_stats_partials(int64_t M, int N, int K);
+/* Plain form (affine+ReLU prologue, no fused reduction).  N % 32 == 0 (N <= 64) or N % 64 == 0,
+ * N <= 256, K % 32 == 0, K <= 256.  The resident weight slice is loaded by TMA
+ * (cp.async.bulk.tensor over a 2-D view of the image).                                           */
 int spg_tc_gemm(const float* A, int64_t lda, const float* weight_image, const float* bias, float* C,
                 int64_t ldc, int64_t M, int N, int K, const float* a_scale, const float* a_shift,
-                int a_relu, float* stats_ws, spg_stream_t stream);
+                int a_relu, spg_stream_t stream);
+/* Full form: the BatchNorm bookkeeping of a training step fused on both sides of the product
+ * (replaces nn.BatchNorm1d's statistics pass and autograd's BatchNorm/ReLU backward kernels around
+ * the Conv1d(k=1) stacks of learning/pointnet.py:27-37,83-96).
+ *   prologue  a2 == NULL : f(A) = relu?(A*a_scale + a_shift)                     (forward)
+ *             a2 != NULL : A = dL/d(activation), a2 = raw layer output y [M,K] (ld lda2);
+ *                          f = a_scale*(gz - s1/M - xhat*s2/M), gz = relu'(y*a_scale+a_shift)*A,
+ *                          xhat = (y-a_mean)/sqrt(a_var+a_eps), a_s12 = s1[K] | s2[K];
+ *                          dy_out (optional, ld lddy) receives f(A) for the weight-gradient kernel
+ *   epilogue  0 none
+ *             1 batch statistics of C: mean_out/var_out[N] (biased) and, if scale_out != NULL, the
+ *               fold scale = gamma/sqrt(var+eps), shift = beta - mean*scale, running statistics
+ *               (momentum, unbiased variance) and num_batches_tracked += 1
+ *             2 BatchNorm-backward sums of the layer BELOW (C is its dL/d(activation), e_y its raw
+ *               output [M,N]): e_s12 = sum_m gz | sum_m gz*xhat with that layer's e_scale/e_shift/
+ *               e_mean/e_var/e_relu
+ * partials_ws: spg_tc_gemm_max_partials() * N * 3 floats.  The reductions finish inside the kernel
+ * (last CTA merges the per-CTA partials in a fixed order: deterministic).                          */
+int spg_tc_gemm_max_partials(void);
+int spg_tc_gemm_ex(const float* A, int64_t lda, const float* weight_image, const float* bias, float* C,
+                   int64_t ldc, int64_t M, int N, int K,
+                   const float* a_scale, const float* a_shift, int a_relu,
+                   const float* a2, int64_t lda2, const float* a_mean, const float* a_var,
+                   const float* a_s12, float a_eps, float* dy_out, int64_t lddy,
+                   int epilogue, float* partials_ws,
+                   float* mean_out, float* var_out, const float* gamma, const float* beta, float eps,
+                   float* scale_out, float* shift_out, float* running_mean, float* running_var,
+                   int64_t* num_batches_tracked, float momentum,
+                   const float* e_y, int64_t e_ldy, const float* e_scale, const float* e_shift,
+                   const float* e_mean, const float* e_var, float e_eps, int e_relu, float* e_s12,
+                   spg_stream_t stream);
 
 /* Weight gradient of a point-wise layer on the tensor cores (3xTF32, fp32-equivalent):
  *   dW[co,ci] = sum_m dY[m,co] * f(P)[m,ci],  f = affine(p_scale,p_shift)+ReLU of P's producer.

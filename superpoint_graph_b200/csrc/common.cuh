@@ -92,12 +92,6 @@ bool vec_act_bwd_apply(const float* G, int64_t ldg, const float* Y, int64_t ldy,
 bool vec_affine_act(const float* Y, int64_t ldy, const float* scale, const float* shift, int relu,
                     float* out, int64_t ldo, int64_t M, int C, cudaStream_t s, int* rc);
 
-// second-generation tcgen05 GEMM (tc_gemm2.cu): persistent, warp-specialised, weights resident
-int tc_gemm2_try(const float* A, int64_t lda, const float* weight_image, const float* bias, float* C,
-                 int64_t ldc, int64_t M, int N, int K, const float* a_scale, const float* a_shift,
-                 int a_relu, float* stats_ws, cudaStream_t s, bool* handled);
-bool tc_gemm2_handles(int N, int K);
-
 }  // namespace spg
 
 #define SPG_LAUNCH(kid, stream_, kernel, grid, block, smem, ...)            \

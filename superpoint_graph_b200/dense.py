@@ -174,16 +174,27 @@ def _accumulate_grad(prm, g):
 def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_g=False, pooled=None):
     """G: gradient w.r.t. the chain's final *activated* output [M, C_last].
     `grads` (list aligned with params) is filled in place.  Returns the gradient w.r.t. the
-    chain input's activated value [M, cin_0] (or None)."""
+    chain input's activated value [M, cin_0] (or None).
+
+    Where the data-gradient GEMM of a layer runs on the tcgen05 kernel, the BatchNorm/ReLU backward
+    around it is fused into that ONE launch: the prologue turns dL/d(activation) into dL/dY on the
+    fly (and stores it once for the weight-gradient kernel), the epilogue reduces the BatchNorm-
+    backward sums of the layer below from the tile it has just produced.  The stand-alone
+    act_bwd_reduce / act_bwd_apply kernels remain for the small-row chains."""
+    red = None  # s1|s2 of the current layer, if the GEMM that produced G already reduced them
     for li in range(len(specs) - 1, -1, -1):
         sp = specs[li]
         cur, nxt, mean, var = saved[li]
         C = sp.cout
+        Wp = params[sp.w]
+        want_dx = li > 0 or need_input_grad
         fused_pool = (pooled is not None and li == len(specs) - 1 and sp.bn is not None
                       and mean is not None and C % 4 == 0)
         if G is None and not fused_pool:  # generic path: materialise the dense pooled gradient
             gp, ldgp, argmax, Bc, Lc = pooled
             G, ldg, own_g = ops.segmax_bwd(gp, ldgp, argmax, Bc, Lc, C), C, True
+        lazy = None  # BatchNorm backward deferred into the data-gradient GEMM's prologue
+        dY, ldy = None, C
         if fused_pool:
             # the chain's output went through a max-pool: fused pool-backward + BN/ReLU backward
             gp, ldgp, argmax, Bc, Lc = pooled
@@ -192,29 +203,31 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
             if sp.gamma is not None:
                 grads[sp.gamma] = s2
                 grads[sp.beta] = s1
-            ldy = C
         elif sp.bn is not None:
             eps = sp.bn.eps
-            s1, s2 = ops.act_bwd_reduce(G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var,
-                                        eps, nxt.relu, M, C)
+            s12 = red if red is not None else ops.act_bwd_reduce(
+                G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var, eps, nxt.relu, M, C)
+            s1, s2 = s12[:C], s12[C:]
             if sp.gamma is not None:
                 grads[sp.gamma] = s2
                 grads[sp.beta] = s1
-            out = G if (own_g and ldg == C) else None
-            dY = ops.act_bwd_apply(G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var, eps,
-                                   nxt.relu, True, s1, s2, M, C, out=out, ldo=C)
-            ldy = C
+            if (want_dx and ldg % 4 == 0 and nxt.ld % 4 == 0 and mean is not None
+                    and ops.tc_supported(M, sp.cin, sp.cout, ldg, sp.cin)):
+                lazy = (nxt.raw, nxt.ld, nxt.scale, nxt.shift, nxt.relu, mean, var, s12, eps, True)
+            else:
+                out = G if (own_g and ldg == C) else None
+                dY = ops.act_bwd_apply(G, ldg, nxt.raw, nxt.ld, nxt.scale, nxt.shift, mean, var, eps,
+                                       nxt.relu, True, s1, s2, M, C, out=out, ldo=C)
         elif sp.relu:
             out = G if (own_g and ldg == C) else None
             dY = ops.act_bwd_apply(G, ldg, nxt.raw, nxt.ld, None, None, None, None, 0.0, True,
                                    False, None, None, M, C, out=out, ldo=C)
-            ldy = C
         else:
             dY, ldy = G, ldg
-        # weight gradient: dW[cout, cin] = dY^T [cout, M] * act(prev)[M, cin]
-        Wp = params[sp.w]
+        red = None
 
-        def weight_grads(dY=dY, ldy=ldy, cur=cur, nxt=nxt, mean=mean, sp=sp, Wp=Wp, C=C):
+        # weight gradient: dW[cout, cin] = dY^T [cout, M] * act(prev)[M, cin]
+        def weight_grads(dY, ldy, cur=cur, nxt=nxt, mean=mean, sp=sp, Wp=Wp, C=C):
             kpad = _padded_k(sp.cin, cur.ld)
             if ops.tc_dw_supported(M, sp.cout, kpad, ldy, cur.ld) and (kpad == sp.cin or not cur.pending):
                 dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, kpad, p_aff=cur.aff())
@@ -233,29 +246,50 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
                     db = ops.colsum(dY, ldy, M, C)
             return dW.view(Wp.shape), db
 
-        side = ops.SIDE[0]
-        if side is None:
-            grads[sp.w], db = weight_grads()
-            if sp.b is not None:
-                grads[sp.b] = db
-        else:
-            # Trainer mode: nothing downstream reads a weight gradient, so it runs on the side
-            # stream while this stream goes on with the data gradient and the next layer.  The
-            # result goes straight to .grad (see _RecurrentECCFunction.backward).
-            with side.fork(dY, saved[li]):
-                dW, db = weight_grads()
-                _accumulate_grad(Wp, dW)
+        def run_weight_grads(dY, ldy):
+            side = ops.SIDE[0]
+            if side is None:
+                grads[sp.w], db = weight_grads(dY, ldy)
                 if sp.b is not None:
-                    if db is _ZEROS.get((C, dY.device.index)):
-                        db = db.clone()  # .grad must not alias the shared zero vector
-                    _accumulate_grad(params[sp.b], db)
-        if li > 0 or need_input_grad:
-            if ops.tc_supported(M, sp.cin, sp.cout, ldy, sp.cin):
-                G = ops.tc_gemm(dY, ldy, _w2d(Wp), sp.cin, True, M, sp.cin, sp.cout)
+                    grads[sp.b] = db
             else:
-                G = ops.gemm(dY, ldy, True, _w2d(Wp), sp.cin, False, M, sp.cin, sp.cout)
-            ldg = sp.cin
-            own_g = True
+                # Trainer mode: nothing downstream reads a weight gradient, so it runs on the side
+                # stream while this stream goes on with the data gradient and the next layer.  The
+                # result goes straight to .grad (see _RecurrentECCFunction.backward).
+                with side.fork(dY, saved[li]):
+                    dW, db = weight_grads(dY, ldy)
+                    _accumulate_grad(Wp, dW)
+                    if sp.b is not None:
+                        if db is _ZEROS.get((C, dY.device.index)):
+                            db = db.clone()  # .grad must not alias the shared zero vector
+                        _accumulate_grad(params[sp.b], db)
+
+        if lazy is None:
+            run_weight_grads(dY, ldy)  # forked before the data gradient: the side stream starts earlier
+        Gn = None
+        if want_dx:
+            if lazy is not None or ops.tc_supported(M, sp.cin, sp.cout, ldy, sp.cin):
+                bnred = None
+                if li > 0 and specs[li - 1].bn is not None and saved[li - 1][2] is not None and cur.ld % 4 == 0:
+                    # `cur` is the layer below's deferred output: its raw y, BatchNorm fold and ReLU
+                    bnred = (cur.raw, cur.ld, cur.scale, cur.shift, saved[li - 1][2], saved[li - 1][3],
+                             specs[li - 1].bn.eps, cur.relu)
+                res = ops.tc_gemm(G if lazy is not None else dY, ldg if lazy is not None else ldy,
+                                  _w2d(Wp), sp.cin, True, M, sp.cin, sp.cout, bnbwd=lazy, bnred=bnred)
+                res = list(res) if isinstance(res, tuple) else [res]
+                Gn = res.pop(0)
+                if lazy is not None:
+                    dY, ldy = res.pop(0), C
+                if bnred is not None:
+                    red = res.pop(0)
+            else:
+                Gn = ops.gemm(dY, ldy, True, _w2d(Wp), sp.cin, False, M, sp.cin, sp.cout)
+        elif lazy is not None:  # (cannot happen: lazy implies want_dx)
+            raise AssertionError
+        if lazy is not None:
+            run_weight_grads(dY, ldy)
+        if want_dx:
+            G, ldg, own_g = Gn, sp.cin, True
         else:
             G = None
     return G

@@ -341,33 +341,81 @@ def prepack(jobs):
         PACK_CACHE[k] = img
 
 
+def _weight_image(W, ldw, transpose, N, K, kv, dev):
+    key = (W.data_ptr(), int(ldw), int(bool(transpose)), int(N), int(K), int(kv))
+    img = PACK_CACHE.get(key)
+    if img is None:
+        img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
+        _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, kv, img, _lib.current_stream())
+        if PACK_LEARN[0] is not None:
+            PACK_LEARN[0][key] = (W, int(ldw), bool(transpose), int(N), int(K), kv)
+    return img
+
+
 def tc_gemm(A, lda, W, ldw, transpose, M, N, K, bias=None, a_aff=None, stats=False, k_valid=None,
-            fold=None):
-    """C[M,N] = f(A)[M,K] B[N,K]^T + bias on the tcgen05 3xTF32 kernel.
-    transpose=False: B = W ([N,K], ld ldw); True: B = W^T with W [K,N]."""
+            fold=None, bnbwd=None, bnred=None):
+    """C[M,N] = f(A)[M,K] B[N,K]^T + bias on the tcgen05 3xTF32 kernel (spg_tc_gemm_ex).
+    transpose=False: B = W ([N,K], ld ldw); True: B = W^T with W [K,N].
+
+    stats / fold: batch statistics of C (and the BatchNorm fold) finished inside the kernel; returns
+        (C, mean, var[, scale, shift]).
+    bnbwd = (Y, ldy, scale, shift, relu, mean, var, s12, eps, want_dy): A is dL/d(activation) of a
+        BatchNorm+ReLU layer whose raw output is Y; the prologue turns it into dL/dY on the fly.
+        With want_dy the kernel also stores dL/dY [M,K] (for the weight-gradient kernel).
+    bnred = (Y2, ldy2, scale2, shift2, mean2, var2, eps2, relu2): C is dL/d(activation) of the layer
+        below; its BatchNorm-backward sums s1|s2 [2N] come out of the epilogue.
+    Returns C, or a tuple (C, [mean, var, [scale, shift]], [dY], [s12]) in that order."""
     _need_cuda(A, W)
     dev = A.device
     kv = int(K if k_valid is None else k_valid)
-    img = PACK_CACHE.get((W.data_ptr(), int(ldw), int(bool(transpose)), int(N), int(K), kv))
-    if img is None:
-        img = torch.empty(2 * N * K, dtype=torch.float32, device=dev)
-        _lib.call("spg_tc_pack_weights", W, ldw, int(bool(transpose)), N, K, kv, img,
-                  _lib.current_stream())
-        if PACK_LEARN[0] is not None:
-            PACK_LEARN[0][(W.data_ptr(), int(ldw), int(bool(transpose)), int(N), int(K), kv)] = (
-                W, int(ldw), bool(transpose), int(N), int(K), kv)
+    img = _weight_image(W, ldw, transpose, N, K, kv, dev)
     out = torch.empty((M, N), dtype=torch.float32, device=dev)
     a_s, a_t, a_r = a_aff if a_aff is not None else (None, None, False)
-    tiles = int(_lib.lib().spg_tc_gemm_stats_partials(int(M), int(N), int(K)))
-    sws = workspace((tiles + tiles // 256 + 2) * N * 3, dev, slot=1) if stats else None
+    a2 = a_mean = a_var = a_s12 = dy = None
+    lda2 = lddy = 0
+    a_eps = 0.0
+    if bnbwd is not None:
+        a2, lda2, a_s, a_t, a_r, a_mean, a_var, a_s12, a_eps, want_dy = bnbwd
+        if want_dy:
+            dy = torch.empty((M, K), dtype=torch.float32, device=dev)
+            lddy = K
+    epi, ws = 0, None
+    mean = var = scale = shift = gamma = beta = rm = rv = nbt = None
+    eps = mom = 0.0
+    e = (None, 0, None, None, None, None, 0.0, False)
+    s12 = None
+    if stats:
+        epi = 1
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        var = torch.empty(N, dtype=torch.float32, device=dev)
+        if fold is not None:
+            gamma, beta, eps, rm, rv, nbt, mom = fold
+            scale = torch.empty(N, dtype=torch.float32, device=dev)
+            shift = torch.empty(N, dtype=torch.float32, device=dev)
+    elif bnred is not None:
+        epi = 2
+        e = bnred
+        s12 = torch.empty(2 * N, dtype=torch.float32, device=dev)
+    if epi:
+        ws = workspace(MAX_TC_PARTIALS[0] * N * 3, dev, slot=1)
     GEMM_FLOPS[0] += 2 * M * N * K
     TC_FLOPS[0] += 2 * M * N * K
-    _lib.call("spg_tc_gemm", A, lda, img, bias, out, N, M, N, K, a_s, a_t, int(bool(a_r)), sws,
+    _lib.call("spg_tc_gemm_ex", A, lda, img, bias, out, N, M, N, K, a_s, a_t, int(bool(a_r)),
+              a2, lda2, a_mean, a_var, a_s12, float(a_eps), dy, lddy, epi, ws,
+              mean, var, gamma, beta, float(eps), scale, shift, rm, rv, nbt, float(mom),
+              e[0], e[1], e[2], e[3], e[4], e[5], float(e[6]), int(bool(e[7])), s12,
               _lib.current_stream())
+    res = [out]
     if stats:
-        return (out,) + _merge_stats(sws, tiles, N, M, dev, fold)
-    return out
+        res += [mean, var] + ([scale, shift] if fold is not None else [])
+    if dy is not None:
+        res.append(dy)
+    if s12 is not None:
+        res.append(s12)
+    return res[0] if len(res) == 1 else tuple(res)
 
+
+MAX_TC_PARTIALS = [148]  # spg_tc_gemm_max_partials(): CTAs along the rows = partials per column
 
 TC_FLOPS = [0]  # algorithmic FLOPs through tc_gemm (forward + data gradients)
 DW_FLOPS = [0]  # algorithmic FLOPs through tc_dw (weight gradients)
@@ -438,12 +486,13 @@ def colsum(X, ldx, M, C):
 
 def act_bwd_reduce(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, M, C):
     _need_cuda(G, Y)
+    """-> s12 [2C]: s1 = s12[:C] (sum of the masked gradient), s2 = s12[C:] (same, weighted by xhat)."""
     s12 = torch.empty(2 * C, dtype=torch.float32, device=G.device)
     s1, s2 = s12[:C], s12[C:]  # contiguous pair: one merge launch writes both
     ws = workspace(2 * C * _chunks(M), G.device)
     _lib.call("spg_act_bwd_reduce", G, ldg, Y, ldy, scale, shift, mean, var, float(eps),
               int(bool(relu)), s1, s2, ws, M, C, _lib.current_stream())
-    return s1, s2
+    return s12
 
 
 def act_bwd_apply(G, ldg, Y, ldy, scale, shift, mean, var, eps, relu, has_bn, s1, s2, M, C,

@@ -264,7 +264,8 @@ def test_batch_stats_and_bn_backward(dev, M, C):
     assert int(nbt) == 1
     G = torch.randn(M, C, device=dev)
     a.backward(G)
-    s1, s2 = ops.act_bwd_reduce(G, C, Yf, C, scale, shift, mean, var, 1e-5, True, M, C)
+    s12 = ops.act_bwd_reduce(G, C, Yf, C, scale, shift, mean, var, 1e-5, True, M, C)
+    s1, s2 = s12[:C], s12[C:]
     close(s1, bn.bias.grad, 1e-4, 1e-5)
     close(s2, bn.weight.grad, 1e-4, 1e-4)
     dY = ops.act_bwd_apply(G, C, Yf, C, scale, shift, mean, var, 1e-5, True, True, s1, s2, M, C)

@@ -21,25 +21,25 @@ def timeit(fn, n=20):
     return ts[len(ts) // 2] * 1e3  # us
 
 print("M =", M)
-for (N, K) in [(64, 64), (128, 64), (128, 128), (256, 128), (64, 128), (128, 256)]:
-    A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
+for (N, K) in [(64, 32), (64, 64), (128, 64), (128, 128), (256, 128), (64, 128), (128, 256)]:
+    A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * 0.2; b = torch.randn(N, device=dev)
     sc, sh = torch.rand(K, device=dev), torch.randn(K, device=dev)
-    img = torch.empty(2 * N * K, device=dev)
-    _lib.call("spg_tc_pack_weights", W, K, 0, N, K, K, img, _lib.current_stream())
-    out = torch.empty(M, N, device=dev)
-    tiles = 4 * ((M + 127) // 128)
-    sws = torch.empty((tiles + 64) * N * 3, device=dev)
-    def run(stats=True, pro=True):
-        _lib.call("spg_tc_gemm", A, K, img, b, out, N, M, N, K, sc if pro else None, sh if pro else None, int(pro),
-                  sws if stats else None, _lib.current_stream())
-    t = timeit(run)
-    t2 = timeit(lambda: run(False, False))
-    tp = timeit(lambda: _lib.call("spg_tc_pack_weights", W, K, 0, N, K, K, img, _lib.current_stream()))
+    gamma, beta = torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev)
+    rm, rv, nbt = torch.zeros(N, device=dev), torch.ones(N, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+    fold = (gamma, beta, 1e-5, rm, rv, nbt, 0.1)
+    y, mean, var, scale, shift = ops.tc_gemm(A, K, W, K, False, M, N, K, bias=b, a_aff=(sc, sh, True), stats=True, fold=fold)
+    t = timeit(lambda: ops.tc_gemm(A, K, W, K, False, M, N, K, bias=b, a_aff=(sc, sh, True), stats=True, fold=fold))
+    t2 = timeit(lambda: ops.tc_gemm(A, K, W, K, False, M, N, K, bias=b))
+    G = torch.randn(M, N, device=dev)
+    s12 = ops.act_bwd_reduce(G, N, y, N, scale, shift, mean, var, 1e-5, True, M, N)
+    mA, vA = A.mean(0), A.var(0, unbiased=False)
+    tb = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N, bnbwd=(y, N, scale, shift, True, mean, var, s12, 1e-5, True),
+                                    bnred=(A, K, sc, sh, mA, vA, 1e-5, True)))
     ts = timeit(lambda: ops.gemm(A, K, True, W, K, True, M, N, K, bias=b, a_aff=(sc, sh, True), stats=False))
     fl = 2.0 * M * N * K
     by = 4.0 * M * (N + K)
-    print("fwd N=%3d K=%3d: tc %7.1f us (%6.1f TF/s, %5.2f TB/s) | no stats/prologue %7.1f us | pack %5.1f us | simt %7.1f us"
-          % (N, K, t, fl / t / 1e6, by / t / 1e6, t2, tp, ts))
+    print("N=%3d K=%3d: fwd+stats %7.1f us (%6.1f TF/s, %5.2f TB/s) | plain %7.1f us | bwd dX (BN prologue, dY store, sums) %7.1f us | simt fwd %7.1f us"
+          % (N, K, t, fl / t / 1e6, by / t / 1e6, t2, tb, ts))
 for (co, ci) in [(128, 64), (128, 128), (256, 128), (256, 64)]:
     dY = torch.randn(M, co, device=dev); P = torch.randn(M, ci, device=dev)
     sc, sh = torch.rand(ci, device=dev), torch.randn(ci, device=dev)
@@ -55,10 +55,7 @@ mean, var = ops.colstats(Y, C, M, C)
 scale, shift = ops.bn_fold(mean, var, None, None, 1e-5)
 t = timeit(lambda: ops.act_bwd_reduce(G, C, Y, C, scale, shift, mean, var, 1e-5, True, M, C))
 print("act_bwd_reduce [M,128]: %.1f us (%.2f TB/s)" % (t, 8.0 * M * C / t / 1e6))
-s1, s2 = ops.act_bwd_reduce(G, C, Y, C, scale, shift, mean, var, 1e-5, True, M, C)
+s12 = ops.act_bwd_reduce(G, C, Y, C, scale, shift, mean, var, 1e-5, True, M, C)
+s1, s2 = s12[:C], s12[C:]
 t = timeit(lambda: ops.act_bwd_apply(G, C, Y, C, scale, shift, mean, var, 1e-5, True, True, s1, s2, M, C))
 print("act_bwd_apply  [M,128]: %.1f us (%.2f TB/s)" % (t, 12.0 * M * C / t / 1e6))
-sws = torch.randn((4 * ((M + 127) // 128) + 64) * C * 3, device=dev).abs()
-mo, vo = torch.empty(C, device=dev), torch.empty(C, device=dev)
-t = timeit(lambda: _lib.call("spg_colstats_merge", sws, 4 * ((M + 127) // 128), C, mo, vo, _lib.current_stream()))
-print("colstats_merge %d partials x %d cols: %.1f us" % ((M + 127) // 128, C, t))
