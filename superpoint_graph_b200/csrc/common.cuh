@@ -47,6 +47,7 @@ enum KernelId {
     K_RNN_BWD,
     K_CLOUD_BUILD,
     K_CONFUSION,
+    K_TC_MERGE,
     K_COUNT
 };
 

@@ -24,11 +24,11 @@
 //                            BNBWD  : f = scale*(gz - s1/M - xhat*s2/M)  (backward: A = dL/d(act),
 //                                     A2 = raw output y of the layer; optional side store of f)
 //
-// The column reductions end in the kernel itself: every CTA writes one partial per column, a grid
-// barrier follows (these launches are cooperative), and the <= 148 partials of every column are
-// merged by one warp somewhere in the grid in a fixed order (deterministic) and folded (mean/var/
-// scale/shift/running statistics, or s1/s2) — no merge kernels on the step's critical path
-// (round 1 spent 0.85 of 1.95 ms there).
+// The column reductions leave ONE partial per CTA and column (pivoted sums are carried across the
+// CTA's tiles); a 32-block companion kernel (tc_merge_kernel, same C-ABI call) folds the <= 148
+// partials per column in a fixed order (deterministic) into mean/var/scale/shift/running statistics
+// or s1/s2.  Round 1 wrote a partial per (tile, warp) — 3768 per column — and needed a two-level
+// merge plus separate BatchNorm-backward reduce/apply passes (0.85 of 1.95 ms per step).
 //
 // Reference semantics: nn.Conv1d(k=1)+BatchNorm1d+ReLU stacks of learning/pointnet.py:27-37,83-96
 // and their autograd backward.
@@ -47,7 +47,6 @@ constexpr int T2_KC = 32;
 constexpr int T2_MAX_STAGES = 4;  // the A ring gets as many stages as fit next to the resident weights
 constexpr int T2_EPI_WARPS = 4, T2_PROD_WARPS = 8;  // (8 epilogue warps force 96 regs/thread: measured slower)
 constexpr int T2_THREADS = (T2_EPI_WARPS + 1 + T2_PROD_WARPS) * 32;  // 416
-constexpr int T2_WARPS = T2_THREADS / 32;
 constexpr int T2_A_BYTES = T2_BM * T2_KC * 4;                        // 16 KB (hi or lo)
 constexpr int T2_STAGE_BYTES = 2 * T2_A_BYTES;
 constexpr int T2_EPI_PITCH = 36;  // floats per row of an epilogue transpose tile (16-byte aligned rows)
@@ -73,7 +72,6 @@ struct Tc2Args {
     int64_t lddy;
     int epi;        // EPI_*
     float* part;    // per-CTA partials [gridDim.x][N][3 | 2]
-    unsigned* counter;
     // EPI_STATS outputs (+ optional fold)
     float *mean_out, *var_out;
     const float *gamma, *beta;
@@ -166,7 +164,7 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
     // Register-level prefetch ring: PF chunks of A are in flight per thread (the global-load
     // latency, ~2 us under load, is far longer than one chunk's transform + MMA).  The BNBWD
     // prologue streams two operands, so its ring is half as deep (same register budget).
-    constexpr int PF = PRO == PRO_BNBWD ? 2 : 4;
+    constexpr int PF = PRO == PRO_BNBWD ? 2 : 4;  // (3 spills at the 128-register cap of a 13-warp CTA)
     constexpr int NOPS = PRO == PRO_BNBWD ? 2 : 1;
     float4 q[PF][NOPS][4];
     const int pt = t - (T2_EPI_WARPS + 1) * 32;  // producer thread id 0..255 (negative: other roles)
@@ -378,9 +376,22 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
             const int nv = (int)max((int64_t)0, min((int64_t)32, p.M - row0));
 #pragma unroll 1
             for (int cb = 0; cb < NS / 32; ++cb) {
+                const int col0 = n0 + cb * 32;
+                const int rr = lane >> 3, c4 = lane & 7;
+                // BNRED: the y rows of the layer below are put in flight before the accumulator is
+                // read, so that their global-load latency hides behind tcgen05.ld + the transpose
+                float4 yv[8];
+                if (p.epi == EPI_BNRED) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int rw = itr * 4 + rr;
+                        yv[itr] = rw < nv ? __ldg(reinterpret_cast<const float4*>(
+                                                p.e_y + (row0 + rw) * p.e_ldy + col0 + 4 * c4))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * NS + cb * 32), r);
-                const int col0 = n0 + cb * 32;
                 // lane = row -> shared tile -> (4 rows x 128 B) per store instruction
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -390,7 +401,6 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
                                     __uint_as_float(r[4 * j + 2]) + bias_s[cb * 32 + 4 * j + 2],
                                     __uint_as_float(r[4 * j + 3]) + bias_s[cb * 32 + 4 * j + 3]);
                 __syncwarp();
-                const int rr = lane >> 3, c4 = lane & 7;
                 float4 e_sc, e_sh, e_mu, e_rs;
                 float b1[4] = {0.f, 0.f, 0.f, 0.f}, b2[4] = {0.f, 0.f, 0.f, 0.f};
                 if (p.epi == EPI_BNRED) {
@@ -407,8 +417,7 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
                         *reinterpret_cast<float4*>(p.C + (row0 + rw) * p.ldc + col0 + 4 * c4) = o;
                         if (p.epi == EPI_BNRED) {
                             // BatchNorm-backward sums of the layer below: gz = relu'(y) * g
-                            const float4 y = __ldg(reinterpret_cast<const float4*>(
-                                p.e_y + (row0 + rw) * p.e_ldy + col0 + 4 * c4));
+                            const float4 y = yv[itr];
                             float gx = o.x, gy = o.y, gz = o.z, gw = o.w;
                             if (p.e_relu) {
                                 if (!(fmaf(y.x, e_sc.x, e_sh.x) > 0.f)) gx = 0.f;
@@ -482,7 +491,6 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
     if (p.epi == EPI_NONE) return;
 
     // ---------------- column reductions: CTA partial, then the last CTA merges and folds -------------
-    const int P = (int)gridDim.x;
     if (t < NS) {
         if (p.epi == EPI_STATS) {
             // Chan merge of the 4 row quarters (each: n, pivot + d1/n, d2 - d1^2/n), fixed order
@@ -516,24 +524,18 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
             o[1] = a2;
         }
     }
-    // Grid barrier (reduction launches are cooperative: all CTAs are co-resident), then the merge is
-    // spread over the whole grid: (CTA b, warp w) folds column b + total*w — one L2 round trip per
-    // column instead of a serial walk by one CTA.
-    const unsigned total = gridDim.x * gridDim.y;
-    __threadfence();
-    __syncthreads();
-    if (t == 0) {
-        atomicAdd(p.counter, 1u);
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.counter) : "memory");
-        } while (v < total);
-        __threadfence();
-    }
-    __syncthreads();
-    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
-    // warp per column; lanes stride over the P partials (fixed assignment + xor tree: deterministic)
-    for (int c = (int)(cta + total * warp); c < p.N; c += (int)(total * T2_WARPS)) {
+}
+
+// Second (tiny) kernel of a fused reduction: one warp per column folds the <= 148 per-CTA partials in
+// a fixed order (deterministic) and writes mean/var (+ BatchNorm fold, running statistics) or s1|s2.
+// (An in-kernel grid barrier was tried first: it needs a cooperative launch, which must wait until the
+// WHOLE grid fits on the GPU and thereby serialises against the weight-gradient kernels of the side
+// stream — 2.30 ms per step instead of 1.97.)
+__global__ void __launch_bounds__(256) tc_merge_kernel(const Tc2Args p, int P) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;
+    if (c >= p.N) return;
+    {
         if (p.epi == EPI_STATS) {
             double sn = 0.0, snm = 0.0;
             float pn[5], pm[5], pq[5];  // P <= 148 -> <= 5 partials per lane
@@ -597,15 +599,6 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
             }
         }
     }
-    // re-arm the barrier words for the next launch that draws this slot: the CTA that leaves last
-    // (second ticket) knows that nobody spins on the first word any more
-    if (t == 0) {
-        const unsigned ticket = atomicAdd(p.counter + 1, 1u);
-        if (ticket == total - 1) {
-            p.counter[0] = 0u;
-            p.counter[1] = 0u;
-        }
-    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -641,24 +634,6 @@ static int make_weight_map(CUtensorMap* map, const float* image, int N, int K, i
     return r == CUDA_SUCCESS ? SPG_OK : SPG_E_BADARG;
 }
 
-// grid-barrier words of the fused reductions: a ring of slots so that launches running concurrently
-// on different streams never share one (each slot is re-armed to 0 by the CTA that leaves last)
-static unsigned* next_counter() {
-    constexpr int kRing = 4096;
-    static unsigned* ring[16] = {nullptr};
-    static unsigned cursor[16] = {0};
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!ring[dev]) {
-        // first use must happen outside a stream capture (Trainer.capture warms up eagerly first)
-        if (cudaMalloc(&ring[dev], kRing * sizeof(unsigned)) != cudaSuccess) return nullptr;
-        if (cudaMemset(ring[dev], 0, kRing * sizeof(unsigned)) != cudaSuccess) return nullptr;
-    }
-    return ring[dev] + 2 * (cursor[dev]++ % (kRing / 2));  // a slot = {arrivals, departures}
-}
-
 static inline int fixed_smem(int NS, int K) {
     return (K / T2_KC) * 2 * NS * T2_KC * 4 + (4 * K + NS + 4 * NS + T2_EPI_WARPS * NS * 4) * 4 +
            T2_EPI_WARPS * 32 * T2_EPI_PITCH * 4;
@@ -679,10 +654,6 @@ static int launch_tc2(Tc2Args& a, const float* image, cudaStream_t s) {
     const int nst = stages_for(NS, a.K);
     if (nst < 2) return SPG_E_UNSUPPORTED;
     a.nstages = nst;
-    if (a.epi != EPI_NONE) {
-        a.counter = next_counter();
-        if (!a.counter) return SPG_E_UNSUPPORTED;
-    }
     CUtensorMap map;
     int rc = make_weight_map(&map, image, a.N, a.K, NS);
     if (rc) return rc;
@@ -690,18 +661,10 @@ static int launch_tc2(Tc2Args& a, const float* image, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm2_kernel<NS, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    if (a.epi == EPI_NONE) {
-        SPG_LAUNCH(K_TC_GEMM, s, (tc_gemm2_kernel<NS, PRO>), grid, T2_THREADS, smem, a, map);
-        return launch_status();
-    }
-    // fused reductions end in a grid barrier: cooperative launch (co-residency enforced by the driver)
-    void* kargs[] = {(void*)&a, (void*)&map};
-    {
-        ::spg::LaunchScope _scope(K_TC_GEMM, s);
-        e = cudaLaunchCooperativeKernel((const void*)tc_gemm2_kernel<NS, PRO>, grid, dim3(T2_THREADS), kargs,
-                                        (size_t)smem, s);
-    }
-    if (e != cudaSuccess) return (int)e;
+    SPG_LAUNCH(K_TC_GEMM, s, (tc_gemm2_kernel<NS, PRO>), grid, T2_THREADS, smem, a, map);
+    rc = launch_status();
+    if (rc || a.epi == EPI_NONE) return rc;
+    SPG_LAUNCH(K_TC_MERGE, s, tc_merge_kernel, (unsigned)ceil_div64(a.N, 8), 256, 0, a, (int)gx);
     return launch_status();
 }
 
@@ -751,7 +714,7 @@ int spg_tc_gemm_ex(const float* A, int64_t lda, const float* weight_image, const
     a.N = N; a.K = K; a.a_scale = a_scale; a.a_shift = a_shift; a.a_relu = a_relu;
     a.a_mean = a_mean; a.a_var = a_var; a.a_s12 = a_s12; a.a_eps = a_eps;
     a.dy_out = dy_out; a.lddy = lddy;
-    a.epi = epilogue; a.part = partials_ws; a.counter = nullptr;
+    a.epi = epilogue; a.part = partials_ws;
     a.mean_out = mean_out; a.var_out = var_out; a.gamma = gamma; a.beta = beta;
     a.scale_out = scale_out; a.shift_out = shift_out; a.rmean = running_mean; a.rvar = running_var;
     a.nbt = (long long*)num_batches_tracked; a.eps = eps; a.momentum = momentum;

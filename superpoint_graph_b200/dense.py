@@ -211,7 +211,7 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
             if sp.gamma is not None:
                 grads[sp.gamma] = s2
                 grads[sp.beta] = s1
-            if (want_dx and ldg % 4 == 0 and nxt.ld % 4 == 0 and mean is not None
+            if (ops.USE_FUSED_BNBWD[0] and want_dx and ldg % 4 == 0 and nxt.ld % 4 == 0 and mean is not None
                     and ops.tc_supported(M, sp.cin, sp.cout, ldg, sp.cin)):
                 lazy = (nxt.raw, nxt.ld, nxt.scale, nxt.shift, nxt.relu, mean, var, s12, eps, True)
             else:
@@ -270,7 +270,8 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
         if want_dx:
             if lazy is not None or ops.tc_supported(M, sp.cin, sp.cout, ldy, sp.cin):
                 bnred = None
-                if li > 0 and specs[li - 1].bn is not None and saved[li - 1][2] is not None and cur.ld % 4 == 0:
+                if (ops.USE_FUSED_BNBWD[0] and li > 0 and specs[li - 1].bn is not None
+                        and saved[li - 1][2] is not None and cur.ld % 4 == 0):
                     # `cur` is the layer below's deferred output: its raw y, BatchNorm fold and ReLU
                     bnred = (cur.raw, cur.ld, cur.scale, cur.shift, saved[li - 1][2], saved[li - 1][3],
                              specs[li - 1].bn.eps, cur.relu)

@@ -33,13 +33,18 @@ for (N, K) in [(64, 32), (64, 64), (128, 64), (128, 128), (256, 128), (64, 128),
     G = torch.randn(M, N, device=dev)
     s12 = ops.act_bwd_reduce(G, N, y, N, scale, shift, mean, var, 1e-5, True, M, N)
     mA, vA = A.mean(0), A.var(0, unbiased=False)
-    tb = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N, bnbwd=(y, N, scale, shift, True, mean, var, s12, 1e-5, True),
-                                    bnred=(A, K, sc, sh, mA, vA, 1e-5, True)))
+    bw = (y, N, scale, shift, True, mean, var, s12, 1e-5)
+    tb = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N, bnbwd=bw + (True,), bnred=(A, K, sc, sh, mA, vA, 1e-5, True)))
+    tb1 = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N, bnbwd=bw + (False,)))
+    tb2 = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N, bnbwd=bw + (True,)))
+    tb3 = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N, bnred=(A, K, sc, sh, mA, vA, 1e-5, True)))
+    tb4 = timeit(lambda: ops.tc_gemm(G, N, W, K, True, M, K, N))
+    tb5 = timeit(lambda: ops.tc_gemm(A, K, W, K, False, M, N, K, bias=b, stats=True, fold=fold))
     ts = timeit(lambda: ops.gemm(A, K, True, W, K, True, M, N, K, bias=b, a_aff=(sc, sh, True), stats=False))
     fl = 2.0 * M * N * K
     by = 4.0 * M * (N + K)
-    print("N=%3d K=%3d: fwd+stats %7.1f us (%6.1f TF/s, %5.2f TB/s) | plain %7.1f us | bwd dX (BN prologue, dY store, sums) %7.1f us | simt fwd %7.1f us"
-          % (N, K, t, fl / t / 1e6, by / t / 1e6, t2, tb, ts))
+    print("N=%3d K=%3d: fwd affine+stats %6.1f us (%5.1f TF/s, %4.2f TB/s) | stats only %6.1f | plain %6.1f || bwd dX[M,%d]: all %6.1f | bnbwd %6.1f | bnbwd+dY %6.1f | bnred %6.1f | plain %6.1f || simt fwd %6.1f"
+          % (N, K, t, fl / t / 1e6, by / t / 1e6, tb5, t2, K, tb, tb1, tb2, tb3, tb4, ts))
 for (co, ci) in [(128, 64), (128, 128), (256, 128), (256, 64)]:
     dY = torch.randn(M, co, device=dev); P = torch.randn(M, ci, device=dev)
     sc, sh = torch.rand(ci, device=dev), torch.randn(ci, device=dev)

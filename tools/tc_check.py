@@ -59,8 +59,8 @@ for (M, N, K) in [(1000, 64, 64), (5000, 128, 128), (120576, 128, 256), (120576,
     K2 = 64 if N != 32 else 32
     Wd = torch.randn(N, K2, device=dev) * 0.3        # the layer's weight [cout=N, cin=K2]
     G = torch.randn(M, N, device=dev)
-    yr = yd.clone().requires_grad_(True)
-    xhat = (yr - mu_r) / torch.sqrt(var_r + 1e-5)
+    yr = y.double().clone().requires_grad_(True)  # the kernel's own y: ReLU masks of near-zero elements must agree
+    xhat = (yr - yr.mean(0)) / torch.sqrt(yr.var(0, unbiased=False) + 1e-5)  # batch statistics inside the graph
     act = torch.relu(xhat * gamma.double() + beta.double())
     act.backward(G.double())
     dY_r = yr.grad
