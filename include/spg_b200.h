@@ -96,6 +96,25 @@ int spg_ecc_bwd_x(const void* w, const void* g, const int32_t* tgt_rowptr,
                   int64_t n_in, int64_t n_edges, int c_in, int c_out, int w_is_matrix,
                   int dtype, spg_stream_t stream);
 
+/* Stream variants of the two vector-filter kernels for HBM-sized graphs (C = 32, float32, no idxe):
+ * the (target- resp. source-sorted) edge positions are cut into n_streams runs of about
+ * spg_ecc_stream_edges() positions that end on segment boundaries, bounds[k] = first segment of run k
+ * (int32 [n_streams+1], bounds[0] = 0, bounds[n_streams] = number of segments; host-side searchsorted
+ * of k*spg_ecc_stream_edges() in the CSR row pointer).  Same results as spg_ecc_fwd / spg_ecc_bwd_x up
+ * to summation order.  Extra per-position arrays of the source-sorted order (p = 0..E-1):
+ *   src_node[p] = idxn[src_perm[p]], src_tgt[p] = edge_tgt[src_perm[p]], src_invdeg[p] = 1/deg(src_tgt[p]).
+ * ref: learning/ecc/GraphConvModule.py:59-94 (forward), :96-152 (grad input). */
+int64_t spg_ecc_stream_edges(void);
+int spg_ecc_vv_stream_fwd(const float* x, const float* w, const int32_t* tgt_rowptr,
+                          const int32_t* bounds, int64_t n_streams, const int32_t* edge_tgt,
+                          const int32_t* idxn, float* out, int64_t n_out, int64_t n_edges,
+                          spg_stream_t stream);
+int spg_ecc_vv_stream_bwd_x(const float* w, const float* g, const int32_t* src_rowptr,
+                            const int32_t* bounds, int64_t n_streams, const int32_t* src_node,
+                            const int32_t* src_tgt, const int32_t* src_perm, const float* src_invdeg,
+                            const float* add0, const float* add1, float* grad_x, int64_t n_in,
+                            int64_t n_edges, spg_stream_t stream);
+
 /* ----------------------------------------------------------- GRUCellEx    */
 #define SPG_GRU_LAYERNORM 1
 #define SPG_GRU_INGATE 2

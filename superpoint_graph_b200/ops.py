@@ -91,6 +91,16 @@ class EccGraph(object):
         self.idxe_host = None if idxe is None else idxe.detach().cpu().numpy().astype(np.int32)
         self._dev = {}
 
+    def stream_arrays(self, device):
+        """Device arrays of the stream kernels (spg_ecc_vv_stream_*), built on first use."""
+        device = torch.device(device)
+        key = ("stream", device.type, device.index)
+        if key not in self._dev:
+            host = build_stream_host(self.host, int(_lib.lib().spg_ecc_stream_edges()))
+            self._dev[key] = {k: (torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) else v)
+                              for k, v in host.items()}
+        return self._dev[key]
+
     def to(self, device):
         device = torch.device(device)
         key = (device.type, device.index)
@@ -122,6 +132,37 @@ def build_csr_host(idxn, degs, n_in):
     }
 
 
+def build_stream_host(host, S):
+    """Partition of the target- and source-sorted edge positions into runs of ~S positions that end on
+    segment boundaries, plus the per-position arrays of the source-sorted order (numpy, host side)."""
+    tgt_rowptr, src_rowptr = host["tgt_rowptr"].astype(np.int64), host["src_rowptr"].astype(np.int64)
+    E = int(host["idxn"].shape[0])
+    n_streams = max(1, (E + S - 1) // S)
+    cuts = np.arange(n_streams, dtype=np.int64) * S
+
+    def bounds(rowptr):
+        b = np.searchsorted(rowptr[:-1], cuts, side="left")  # first segment whose first position >= cut
+        b[0] = 0
+        return np.concatenate([b, [rowptr.shape[0] - 1]]).astype(np.int32)
+
+    perm = host["src_perm"].astype(np.int64)
+    src_tgt = host["edge_tgt"][perm]
+    deg = (tgt_rowptr[1:] - tgt_rowptr[:-1]).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        invdeg = (np.float32(1.0) / deg).astype(np.float32)
+    return {"n_streams": n_streams, "tgt_bounds": bounds(tgt_rowptr), "src_bounds": bounds(src_rowptr),
+            "src_node": host["idxn"][perm].astype(np.int32), "src_tgt": src_tgt.astype(np.int32),
+            "src_invdeg": invdeg[src_tgt]}
+
+
+STREAM_MIN_EDGES = [200000]  # below this the graph is L2-resident and latency-bound: warp-per-node kernels
+
+
+def _stream_ok(x, w, graph, c):
+    return (w.dim() == 2 and c == 32 and x.dtype == torch.float32 and graph.idxe_host is None
+            and graph.n_edges >= STREAM_MIN_EDGES[0])
+
+
 # ------------------------------------------------------------------------------ ECC
 def ecc_fwd(x, w, graph, c_out, out=None):
     _need_cuda(x, w)
@@ -136,6 +177,11 @@ def ecc_fwd(x, w, graph, c_out, out=None):
         raise ValueError("weights has %d rows, graph needs %d" % (w.shape[0], n_w))
     if out is None:
         out = torch.empty((graph.n_out, c_out), dtype=x.dtype, device=x.device)
+    if _stream_ok(x, w, graph, c_in) and c_in == c_out and graph.n_in == graph.n_out:
+        st = graph.stream_arrays(x.device)
+        _lib.call("spg_ecc_vv_stream_fwd", x, w, g["tgt_rowptr"], st["tgt_bounds"], st["n_streams"],
+                  g["edge_tgt"], g["idxn"], out, graph.n_out, graph.n_edges, _lib.current_stream())
+        return out
     _lib.call("spg_ecc_fwd", x, w, g["tgt_rowptr"], g["idxn"], g["idxe"], out, graph.n_out,
               graph.n_edges, c_in, c_out, is_mat, _dt(x), _lib.current_stream())
     return out
@@ -170,6 +216,12 @@ def ecc_bwd_x(w, g_out, graph, c_in, add0=None, add1=None):
     is_mat = int(w.dim() == 3)
     c_out = g_out.shape[1]
     gx = torch.empty((graph.n_in, c_in), dtype=w.dtype, device=w.device)
+    if _stream_ok(g_out, w, graph, c_in) and c_in == c_out:
+        st = graph.stream_arrays(w.device)
+        _lib.call("spg_ecc_vv_stream_bwd_x", w, g_out, g["src_rowptr"], st["src_bounds"], st["n_streams"],
+                  st["src_node"], st["src_tgt"], g["src_perm"], st["src_invdeg"], add0, add1, gx,
+                  graph.n_in, graph.n_edges, _lib.current_stream())
+        return gx
     _lib.call("spg_ecc_bwd_x", w, g_out, g["tgt_rowptr"], g["src_rowptr"], g["src_perm"],
               g["edge_tgt"], g["idxe"], add0, add1, gx, graph.n_in, graph.n_edges, c_in, c_out,
               is_mat, _dt(w), _lib.current_stream())
