@@ -1,8 +1,8 @@
 """Copies the UNMODIFIED reference files of the hot path into baseline/_ref/ (git-ignored, shipped to
 the GPU box by gpurun) so that `bench.py --impl reference` can time the reference's own modules
 there.  The reference is pure Python + torch: there is nothing to pip-install (no setup.py /
-pyproject in /root/reference), so the "install" is a verbatim copy of the eight files the path
-imports.  Run by __graft_entry__.build() whenever /root/reference is present.
+pyproject in /root/reference), so the "install" is a verbatim copy of the files the path imports
+ plus the trainer script and its dataset adapters.  Run by __graft_entry__.build() whenever /root/reference is present.
 """
 import os
 import shutil
@@ -22,6 +22,13 @@ FILES = [
     "learning/ecc/GraphPoolModule.py",
     "learning/ecc/cuda_kernels.py",
     "learning/ecc/utils.py",
+    # the trainer and its data side, for the "learning/main.py unchanged" run (compat/run_main.py)
+    "learning/main.py",
+    "learning/spg.py",
+    "learning/s3dis_dataset.py",
+    "learning/custom_dataset.py",
+    "learning/sema3d_dataset.py",
+    "learning/vkitti_dataset.py",
 ]
 
 

@@ -37,27 +37,34 @@ class GraphConvInfo(object):
             self.set_batch(*args, **kwargs)
 
     def set_batch(self, graphs, edge_feat_func):
-        graphs = graphs if isinstance(graphs, (list, tuple)) else [graphs]
-        p = 0
-        idxn, degrees, edge_indexes = [], [], []
-        edgeattrs = defaultdict(list)
+        """Disjoint union of `graphs` in the target-sorted edge order of the reference
+        (ref: learning/ecc/GraphConvInfo.py:33-69), built from arrays: one vertex offset per graph,
+        one per-graph argsort of the target column (numpy's default kind on the same int64 column as the
+        reference, hence the same — not merely an equivalent — permutation), in-degrees by bincount."""
+        graphs = list(graphs) if isinstance(graphs, (list, tuple)) else [graphs]
+        edges = [np.asarray(G.get_edgelist(), dtype=np.int64).reshape(-1, 2) for G in graphs]
+        sizes = np.asarray([G.vcount() for G in graphs], dtype=np.int64)
+        offsets = np.cumsum(sizes) - sizes
+        orders = [E[:, 1].argsort() for E in edges]
+        pairs = [off + E[o] for E, o, off in zip(edges, orders, offsets)]  # [e_g, 2] = (source, target)
+        pairs = np.concatenate(pairs) if pairs else np.zeros((0, 2), dtype=np.int64)
+        total = int(sizes.sum())
+        # every edge attribute, gathered per graph in that graph's sorted order (lists, as igraph yields)
+        names = []
         for G in graphs:
-            E = np.array(G.get_edgelist())
-            idx = E[:, 1].argsort()  # sort by target (numpy default kind, as the reference)
-            idxn.append(p + E[idx, 0])
-            edgeseq = G.es[idx.tolist()]
+            names += [a for a in G.es.attributes() if a not in names]
+        edgeattrs = defaultdict(list)
+        for G, o in zip(graphs, orders):
+            picked = G.es[o.tolist()]
             for a in G.es.attributes():
-                edgeattrs[a] += edgeseq.get_attribute_values(a)
-            degrees += G.indegree(G.vs, loops=True)
-            edge_indexes.append(np.asarray(p + E[idx]))
-            p += G.vcount()
+                edgeattrs[a] += picked.get_attribute_values(a)
         self._edgefeats, self._idxe = edge_feat_func(edgeattrs)
-        self._idxn = torch.LongTensor(np.concatenate(idxn))
+        self._idxn = torch.from_numpy(np.ascontiguousarray(pairs[:, 0]))
         if self._idxe is not None:
             assert self._idxe.numel() == self._idxn.numel()
-        self._degrees = torch.LongTensor(degrees)
+        self._degrees = torch.from_numpy(np.bincount(pairs[:, 1], minlength=total).astype(np.int64))
         self._degrees_gpu = None
-        self._edge_indexes = torch.LongTensor(np.concatenate(edge_indexes).T)
+        self._edge_indexes = torch.from_numpy(np.ascontiguousarray(pairs.T))
         self._graph = None
 
     @classmethod
