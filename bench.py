@@ -733,7 +733,7 @@ def run_b200(args):
                 line["roofline_ecc_scatter"] = ecc_obj
             kv = er["kernels"]["vv_fwd"]
             line["roofline_ecc_scatter_vv"] = {
-                "kernel": "ecc_vv_stream_fwd", "bound": "hbm", "achieved": kv["gbs"], "peak": pk["hbm"],
+                "kernel": "ecc_vv_fwd", "bound": "hbm", "achieved": kv["gbs"], "peak": pk["hbm"],
                 "unit": "GB/s", "frac": kv["frac"], "traffic": (ncu_traffic().get("ecc_vv_fwd") or {}).get("bytes_per_launch"),
                 "workload": "configs[1]/[4] filter mode (vector filters [E,32]): %d superpoints, %d edges, L2 flushed "
                             "before every launch" % (er["nodes"], er["edges"])}

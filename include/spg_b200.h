@@ -96,24 +96,6 @@ int spg_ecc_bwd_x(const void* w, const void* g, const int32_t* tgt_rowptr,
                   int64_t n_in, int64_t n_edges, int c_in, int c_out, int w_is_matrix,
                   int dtype, spg_stream_t stream);
 
-/* Stream variants of the two vector-filter kernels for HBM-sized graphs (C = 32, float32, no idxe):
- * the (target- resp. source-sorted) edge positions are cut into n_streams runs of about
- * spg_ecc_stream_edges() positions that end on segment boundaries, bounds[k] = first segment of run k
- * (int32 [n_streams+1], bounds[0] = 0, bounds[n_streams] = number of segments; host-side searchsorted
- * of k*spg_ecc_stream_edges() in the CSR row pointer).  Same results as spg_ecc_fwd / spg_ecc_bwd_x up
- * to summation order.  Extra per-position arrays of the source-sorted order (p = 0..E-1):
- *   src_node[p] = idxn[src_perm[p]], src_tgt[p] = edge_tgt[src_perm[p]], src_invdeg[p] = 1/deg(src_tgt[p]).
- * ref: learning/ecc/GraphConvModule.py:59-94 (forward), :96-152 (grad input). */
-int64_t spg_ecc_stream_edges(void);
-int spg_ecc_vv_stream_fwd(const float* x, const float* w, const int32_t* tgt_rowptr,
-                          const int32_t* bounds, int64_t n_streams, const int32_t* edge_tgt,
-                          const int32_t* idxn, float* out, int64_t n_out, int64_t n_edges,
-                          spg_stream_t stream);
-int spg_ecc_vv_stream_bwd_x(const float* w, const float* g, const int32_t* src_rowptr,
-                            const int32_t* bounds, int64_t n_streams, const int32_t* src_node,
-                            const int32_t* src_tgt, const int32_t* src_perm, const float* src_invdeg,
-                            const float* add0, const float* add1, float* grad_x, int64_t n_in,
-                            int64_t n_edges, spg_stream_t stream);
 
 /* ----------------------------------------------------------- GRUCellEx    */
 #define SPG_GRU_LAYERNORM 1
@@ -254,13 +236,16 @@ int spg_tc_gemm_ex(const float* A, int64_t lda, const float* weight_image, const
 /* Weight gradient of a point-wise layer on the tensor cores (3xTF32, fp32-equivalent):
  *   dW[co,ci] = sum_m dY[m,co] * f(P)[m,ci],  f = affine(p_scale,p_shift)+ReLU of P's producer.
  * co in {64,128,256}, ci in {32,64,128}; every CTA reduces a slab of points into a partial held in
- * TMEM, workspace >= spg_tc_dw_ctas(M)*co*ci floats, partials are summed in a fixed order.
+ * TMEM, workspace >= spg_tc_dw_ctas(M)*co*ci + ci floats, partials are summed in a fixed order.
+ * centre != 0 (only valid when sum_m dY[m,:] = 0, e.g. dY is the gradient w.r.t. the input of a
+ * batch-statistics BatchNorm): f(P) is centred on column means estimated from the first 2048 points;
+ * the result is mathematically unchanged, its rounding error is not amplified by M*mean(f(P)).
  * C[M,N] = sum_z partials[z,M,N] (+ bias) is also exported on its own (spg_splitk_reduce).       */
 int spg_tc_dw_supported(int64_t M, int co, int ci);
 int spg_tc_dw_ctas(int64_t M);
 int spg_tc_dw(const float* dY, int64_t lddy, const float* P, int64_t ldp, const float* p_scale,
-              const float* p_shift, int p_relu, float* dW, float* workspace, int64_t M, int co, int ci,
-              spg_stream_t stream);
+              const float* p_shift, int p_relu, int centre, float* dW, float* workspace, int64_t M, int co,
+              int ci, spg_stream_t stream);
 int spg_splitk_reduce(const float* partials, int split, int64_t M, int64_t N, const float* bias,
                       float* C, int64_t ldc, spg_stream_t stream);
 
@@ -384,6 +369,17 @@ int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
 int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* label_mode,
                         const int64_t* label_vec, int64_t ld_vec, int64_t* confusion,
                         int64_t* counters, int64_t* pred_out, int64_t n_nodes, int n_classes,
+                        spg_stream_t stream);
+/* Label up-sampling, the step after the path (ref: partition/provider.py:630-635,676-682):
+ * spg_labels_to_points: labels_full[n_ver] (uint8, zero-initialised here) gets labels_red[c] at every
+ *   member point of component c; comp_ptr int64 [n_components+1] is the CSR over point_ids.
+ * spg_nn1_interpolate: exact 1-nearest-neighbour transfer (squared Euclidean distance in float64, ties
+ *   to the lowest index) from the n_ref pruned points to the n_query points; writes the neighbour's
+ *   label (int64) and/or its index (int32).                                                       */
+int spg_labels_to_points(const int64_t* labels_red, const int64_t* comp_ptr, const int64_t* point_ids,
+                         int64_t n_components, uint8_t* labels_full, int64_t n_ver, spg_stream_t stream);
+int spg_nn1_interpolate(const float* xyz_ref, int64_t n_ref, const float* xyz_query, int64_t n_query,
+                        const int64_t* labels_ref, int64_t* labels_out, int32_t* nn_index_out,
                         spg_stream_t stream);
 
 #ifdef __cplusplus

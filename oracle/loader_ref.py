@@ -147,3 +147,29 @@ def eval_bookkeeping(outputs, label_mode, label_vec, n_classes):
     if idx.sum() > 0:
         cm.count_predicted_batch(label_vec[idx, ...], pred[idx])
     return pred, cm.confusion_matrix, int(idx.sum()), int((pred[idx] == label_mode[idx]).sum())
+
+
+# ------------------------------------------------------------------------ label up-sampling
+def reduced_labels2full(labels_red, components, n_ver):
+    """partition/provider.py:630-635."""
+    labels_full = np.zeros((n_ver,), dtype='uint8')
+    for i_com in range(0, len(components)):
+        labels_full[components[i_com]] = labels_red[i_com]
+    return labels_full
+
+
+def interpolate_labels(xyz_up, xyz, labels):
+    """partition/provider.py:676-682: 1-NN label transfer.  The reference calls scikit-learn
+    (NearestNeighbors(n_neighbors=1, algorithm='kd_tree'), unpinned in the reference; 1.x here), whose
+    published algorithm is an exact nearest-neighbour search on float64 copies of the coordinates; it is
+    restated as a blocked brute-force argmin of the float64 squared distance (same result whenever the
+    nearest neighbour is unique)."""
+    if len(labels.shape) > 1 and labels.shape[1] > 1:
+        labels = np.argmax(labels, axis=1)
+    ref = np.asarray(xyz, dtype=np.float64)
+    out = np.empty(xyz_up.shape[0], dtype=np.int64)
+    for i in range(0, xyz_up.shape[0], 2048):
+        q = np.asarray(xyz_up[i:i + 2048], dtype=np.float64)
+        d = ((q[:, None, :] - ref[None, :, :]) ** 2).sum(-1)
+        out[i:i + 2048] = d.argmin(1)
+    return labels[out].flatten(), out

@@ -322,120 +322,6 @@ ecc_mat_bwd_x_kernel(const float4* __restrict__ w, const float4* __restrict__ g,
     grad_x[o] = mine;
 }
 
-// ------------------------------------------------------------ stream kernels (vector filters)
-// Large graphs (the synthetic sweep of configs[4]: 1e5 superpoints, 1e6..2e6 edges) are HBM-bound,
-// and the warp-per-node kernels above are not: a node's ~10 edges hang off a chain of dependent
-// loads (rowptr -> idxn -> rows), so a warp has bytes in flight only a third of its life.  Here the
-// edge list is cut into streams of ~64 consecutive edges whose ends are moved to segment boundaries
-// (host-side searchsorted over the CSR row pointer).  A stream belongs to 8 lanes (one float4 each of
-// the 32 channels): they walk the stream edge by edge with a 4-deep register prefetch ring, keep the
-// running sum of the current segment in registers and flush it when the segment id changes — the
-// "warp-level partial reduction over an edge-sorted CSR" with no cross-lane traffic at all.  The
-// per-position indices of a block's 32 streams are staged in shared memory by coalesced loads first,
-// so no load in the main loop depends on another global load.  Every segment is owned by exactly one
-// stream: no atomics, deterministic; zero-degree segments inside a stream's range are written too.
-//   MODE 0 forward   : segment = target node,  out[t] = (1/deg_t) sum_e x[src_e] * w[e]
-//   MODE 1 grad input: segment = source node,  positions follow the source-sorted permutation,
-//                      out[j] = add0 + add1 + sum_p w[perm_p] * g[tgt_p] * invdeg_p
-constexpr int kStreamEdges = 64;
-constexpr int kStreamsPerBlock = 32;
-constexpr int kStreamCap = kStreamsPerBlock * kStreamEdges + 512;  // staged positions per block
-
-template <int MODE>
-__global__ void __launch_bounds__(256)
-ecc_vv_stream_kernel(const float4* __restrict__ rows, const float4* __restrict__ w,
-                     const int* __restrict__ seg_rowptr, const int* __restrict__ bounds, int n_streams,
-                     const int* __restrict__ seg_of, const int* __restrict__ gidx,
-                     const int* __restrict__ wrow, const float* __restrict__ fac,
-                     const float4* __restrict__ add0, const float4* __restrict__ add1,
-                     float4* __restrict__ out) {
-    __shared__ int s_seg[kStreamCap], s_gidx[kStreamCap];
-    __shared__ int s_wrow[MODE == 1 ? kStreamCap : 1];
-    __shared__ float s_fac[MODE == 1 ? kStreamCap : 1];
-    const int kb = blockIdx.x * kStreamsPerBlock;
-    const int kl = min(kb + kStreamsPerBlock, n_streams);
-    const int PA = seg_rowptr[bounds[kb]], PB = seg_rowptr[bounds[kl]];
-    const bool staged = PB - PA <= kStreamCap;
-    if (staged) {
-        for (int i = threadIdx.x; i < PB - PA; i += 256) {
-            s_seg[i] = __ldg(seg_of + PA + i);
-            s_gidx[i] = __ldg(gidx + PA + i);
-            if (MODE == 1) {
-                s_wrow[i] = __ldg(wrow + PA + i);
-                s_fac[i] = __ldg(fac + PA + i);
-            }
-        }
-    }
-    __syncthreads();
-    const int k = kb + (threadIdx.x >> 3), sub = threadIdx.x & 7;
-    if (k >= kl) return;
-    const int sa = bounds[k], sb = bounds[k + 1];
-    const int pa = seg_rowptr[sa], pb = seg_rowptr[sb];
-    auto SEG = [&](int p) { return staged ? s_seg[p - PA] : __ldg(seg_of + p); };
-    auto GIDX = [&](int p) { return staged ? s_gidx[p - PA] : __ldg(gidx + p); };
-    constexpr int D = 4;
-    float4 wv[D], xv[D];
-    auto issue = [&](int p, int d) {
-        const int gi = GIDX(p);
-        int64_t wr = p;
-        if (MODE == 1) wr = staged ? s_wrow[p - PA] : __ldg(wrow + p);
-        wv[d] = MODE == 0 ? ld_stream4(w + wr * kG + sub) : __ldg(w + wr * kG + sub);
-        xv[d] = __ldg(rows + (int64_t)gi * kG + sub);
-    };
-#pragma unroll
-    for (int d = 0; d < D; ++d)
-        if (pa + d < pb) issue(pa + d, d);
-    int cur = -1, cnt = 0;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto write = [&](int node, float4 v, int n) {
-        if (MODE == 0) {
-            if (n > 0) {
-                const float dn = (float)n;
-                v.x /= dn; v.y /= dn; v.z /= dn; v.w /= dn;
-            }
-        } else {
-            if (add0) {
-                const float4 a = add0[(int64_t)node * kG + sub];
-                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            }
-            if (add1) {
-                const float4 a = add1[(int64_t)node * kG + sub];
-                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            }
-        }
-        out[(int64_t)node * kG + sub] = v;
-    };
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = pa; p < pb; p += D) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const int q = p + d;
-            if (q < pb) {
-                const int sg = SEG(q);
-                if (sg != cur) {
-                    if (cur >= 0) write(cur, acc, cnt);
-                    for (int z = cur < 0 ? sa : cur + 1; z < sg; ++z) write(z, zero4, 0);
-                    cur = sg;
-                    cnt = 0;
-                    acc = zero4;
-                }
-                if (MODE == 0) {
-                    acc = fma4(xv[d], wv[d], acc);
-                } else {
-                    const float f = staged ? s_fac[q - PA] : __ldg(fac + q);
-                    float4 gv = xv[d];
-                    gv.x *= f; gv.y *= f; gv.z *= f; gv.w *= f;
-                    acc = fma4(wv[d], gv, acc);
-                }
-                ++cnt;
-                if (q + D < pb) issue(q + D, d);
-            }
-        }
-    }
-    if (cur >= 0) write(cur, acc, cnt);
-    for (int z = cur < 0 ? sa : cur + 1; z < sb; ++z) write(z, zero4, 0);
-}
-
 // ------------------------------------------------------------ generic kernels
 // Any widths, float32/float64, optional idxe.  One thread per output element.
 
@@ -670,46 +556,6 @@ int spg_ecc_bwd_x(const void* w, const void* g, const int32_t* tgt_rowptr,
                    edge_tgt, idxe, (const double*)add0, (const double*)add1, (double*)grad_x,
                    n_in, c_in, c_out, w_is_matrix);
     }
-    return launch_status();
-}
-
-int64_t spg_ecc_stream_edges(void) { return kStreamEdges; }
-
-/* see include/spg_b200.h */
-int spg_ecc_vv_stream_fwd(const float* x, const float* w, const int32_t* tgt_rowptr,
-                          const int32_t* bounds, int64_t n_streams, const int32_t* edge_tgt,
-                          const int32_t* idxn, float* out, int64_t n_out, int64_t n_edges,
-                          spg_stream_t stream) {
-    if (n_out < 0 || n_edges < 0 || n_streams < 0) return SPG_E_BADARG;
-    if (n_out == 0) return SPG_OK;
-    if (!x || !w || !tgt_rowptr || !bounds || !edge_tgt || !idxn || !out || n_streams < 1) return SPG_E_BADARG;
-    if (!aligned16(x) || !aligned16(w) || !aligned16(out)) return SPG_E_ALIGN;
-    if (n_out >= (1ll << 31) || n_edges >= (1ll << 31)) return SPG_E_UNSUPPORTED;
-    const int64_t blocks = ceil_div64(n_streams, kStreamsPerBlock);
-    SPG_LAUNCH(K_ECC_VV_FWD, (cudaStream_t)stream, ecc_vv_stream_kernel<0>, (unsigned)blocks, 256, 0,
-               (const float4*)x, (const float4*)w, tgt_rowptr, bounds, (int)n_streams, edge_tgt, idxn,
-               (const int*)nullptr, (const float*)nullptr, (const float4*)nullptr, (const float4*)nullptr,
-               (float4*)out);
-    return launch_status();
-}
-
-int spg_ecc_vv_stream_bwd_x(const float* w, const float* g, const int32_t* src_rowptr,
-                            const int32_t* bounds, int64_t n_streams, const int32_t* src_node,
-                            const int32_t* src_tgt, const int32_t* src_perm, const float* src_invdeg,
-                            const float* add0, const float* add1, float* grad_x, int64_t n_in,
-                            int64_t n_edges, spg_stream_t stream) {
-    if (n_in < 0 || n_edges < 0 || n_streams < 0) return SPG_E_BADARG;
-    if (n_in == 0) return SPG_OK;
-    if (!w || !g || !src_rowptr || !bounds || !src_node || !src_tgt || !src_perm || !src_invdeg || !grad_x ||
-        n_streams < 1)
-        return SPG_E_BADARG;
-    if (!aligned16(w) || !aligned16(g) || !aligned16(grad_x) || !aligned16(add0) || !aligned16(add1))
-        return SPG_E_ALIGN;
-    if (n_in >= (1ll << 31) || n_edges >= (1ll << 31)) return SPG_E_UNSUPPORTED;
-    const int64_t blocks = ceil_div64(n_streams, kStreamsPerBlock);
-    SPG_LAUNCH(K_ECC_VV_BWD_X, (cudaStream_t)stream, ecc_vv_stream_kernel<1>, (unsigned)blocks, 256, 0,
-               (const float4*)g, (const float4*)w, src_rowptr, bounds, (int)n_streams, src_node, src_tgt,
-               src_perm, src_invdeg, (const float4*)add0, (const float4*)add1, (float4*)grad_x);
     return launch_status();
 }
 

@@ -220,6 +220,72 @@ confusion_count_kernel(const float* __restrict__ logits, int64_t ldl,
     }
 }
 
+// ------------------------------------------------------------------ label up-sampling
+// Step after the path (partition/provider.py:630-687): predictions live on
+// superpoints of a PRUNED cloud; the full cloud gets them by (a) scattering every superpoint's label
+// to its member points and (b) exact 1-nearest-neighbour transfer from the pruned to the full cloud.
+// The reference does (b) with scikit-learn's kd-tree in float64; here a thread owns a query point,
+// the reference points stream through shared memory as doubles, and the squared distance is formed
+// in float64 exactly as sklearn does ((x-y) exact for float32 inputs), so the neighbour index is the
+// same whenever the nearest neighbour is unique; ties go to the lowest index.
+constexpr int kNnTile = 1024;
+
+__global__ void __launch_bounds__(256)
+nn1_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ qry, int64_t n_q,
+           const int64_t* __restrict__ labels_ref, int64_t* __restrict__ labels_out,
+           int32_t* __restrict__ idx_out) {
+    __shared__ double sx[kNnTile], sy[kNnTile], sz[kNnTile];
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double qx = 0.0, qy = 0.0, qz = 0.0;
+    if (q < n_q) {
+        qx = (double)qry[q * 3];
+        qy = (double)qry[q * 3 + 1];
+        qz = (double)qry[q * 3 + 2];
+    }
+    double best = 1.0e300;
+    int64_t arg = 0;
+    for (int64_t base = 0; base < n_ref; base += kNnTile) {
+        const int n = (int)min((int64_t)kNnTile, n_ref - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            sx[i] = (double)ref[(base + i) * 3];
+            sy[i] = (double)ref[(base + i) * 3 + 1];
+            sz[i] = (double)ref[(base + i) * 3 + 2];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const double dx = qx - sx[i], dy = qy - sy[i], dz = qz - sz[i];
+            const double d = dx * dx + dy * dy + dz * dz;
+            if (d < best) {
+                best = d;
+                arg = base + i;
+            }
+        }
+    }
+    if (q < n_q) {
+        if (idx_out) idx_out[q] = (int32_t)arg;
+        if (labels_out) labels_out[q] = labels_ref[arg];
+    }
+}
+
+// labels_full[point_ids[j]] = labels_red[component of j]; comp_ptr is the CSR over the concatenated
+// member lists (one warp-strided pass; later components overwrite earlier ones as the Python loop does
+// — members are disjoint in every SPG file).
+__global__ void __launch_bounds__(256)
+labels_to_points_kernel(const int64_t* __restrict__ labels_red, const int64_t* __restrict__ comp_ptr,
+                        const int64_t* __restrict__ point_ids, int64_t n_comp,
+                        uint8_t* __restrict__ labels_full, int64_t n_ver) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_comp) return;
+    const uint8_t lab = (uint8_t)labels_red[c];
+    for (int64_t j = comp_ptr[c] + lane; j < comp_ptr[c + 1]; j += 32) {
+        const int64_t v = point_ids[j];
+        if (v >= 0 && v < n_ver) labels_full[v] = lab;
+    }
+}
+
 }  // namespace spg
 
 using namespace spg;
@@ -275,6 +341,34 @@ int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* l
                logits, ld_logits, label_mode, label_vec, ld_vec,
                reinterpret_cast<unsigned long long*>(confusion),
                reinterpret_cast<unsigned long long*>(counters), pred_out, n_nodes, n_classes);
+    return launch_status();
+}
+
+int spg_nn1_interpolate(const float* xyz_ref, int64_t n_ref, const float* xyz_query, int64_t n_query,
+                        const int64_t* labels_ref, int64_t* labels_out, int32_t* nn_index_out,
+                        spg_stream_t stream) {
+    if (n_ref < 0 || n_query < 0) return SPG_E_BADARG;
+    if (n_query == 0) return SPG_OK;
+    if (n_ref == 0 || !xyz_ref || !xyz_query || (!labels_out && !nn_index_out)) return SPG_E_BADARG;
+    if (labels_out && !labels_ref) return SPG_E_BADARG;
+    if (n_ref >= (1ll << 31)) return SPG_E_UNSUPPORTED;
+    SPG_LAUNCH(K_CONFUSION, (cudaStream_t)stream, nn1_kernel, (unsigned)ceil_div64(n_query, 256), 256, 0,
+               xyz_ref, n_ref, xyz_query, n_query, labels_ref, labels_out, nn_index_out);
+    return launch_status();
+}
+
+int spg_labels_to_points(const int64_t* labels_red, const int64_t* comp_ptr, const int64_t* point_ids,
+                         int64_t n_components, uint8_t* labels_full, int64_t n_ver, spg_stream_t stream) {
+    if (n_components < 0 || n_ver < 0) return SPG_E_BADARG;
+    if (n_ver == 0) return SPG_OK;
+    if (!labels_full) return SPG_E_BADARG;
+    cudaError_t e = cudaMemsetAsync(labels_full, 0, (size_t)n_ver, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    if (n_components == 0) return SPG_OK;
+    if (!labels_red || !comp_ptr || !point_ids) return SPG_E_BADARG;
+    SPG_LAUNCH(K_CONFUSION, (cudaStream_t)stream, labels_to_points_kernel,
+               (unsigned)ceil_div64(n_components * 32, 256), 256, 0, labels_red, comp_ptr, point_ids,
+               n_components, labels_full, n_ver);
     return launch_status();
 }
 

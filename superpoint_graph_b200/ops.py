@@ -91,16 +91,6 @@ class EccGraph(object):
         self.idxe_host = None if idxe is None else idxe.detach().cpu().numpy().astype(np.int32)
         self._dev = {}
 
-    def stream_arrays(self, device):
-        """Device arrays of the stream kernels (spg_ecc_vv_stream_*), built on first use."""
-        device = torch.device(device)
-        key = ("stream", device.type, device.index)
-        if key not in self._dev:
-            host = build_stream_host(self.host, int(_lib.lib().spg_ecc_stream_edges()))
-            self._dev[key] = {k: (torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) else v)
-                              for k, v in host.items()}
-        return self._dev[key]
-
     def to(self, device):
         device = torch.device(device)
         key = (device.type, device.index)
@@ -132,37 +122,6 @@ def build_csr_host(idxn, degs, n_in):
     }
 
 
-def build_stream_host(host, S):
-    """Partition of the target- and source-sorted edge positions into runs of ~S positions that end on
-    segment boundaries, plus the per-position arrays of the source-sorted order (numpy, host side)."""
-    tgt_rowptr, src_rowptr = host["tgt_rowptr"].astype(np.int64), host["src_rowptr"].astype(np.int64)
-    E = int(host["idxn"].shape[0])
-    n_streams = max(1, (E + S - 1) // S)
-    cuts = np.arange(n_streams, dtype=np.int64) * S
-
-    def bounds(rowptr):
-        b = np.searchsorted(rowptr[:-1], cuts, side="left")  # first segment whose first position >= cut
-        b[0] = 0
-        return np.concatenate([b, [rowptr.shape[0] - 1]]).astype(np.int32)
-
-    perm = host["src_perm"].astype(np.int64)
-    src_tgt = host["edge_tgt"][perm]
-    deg = (tgt_rowptr[1:] - tgt_rowptr[:-1]).astype(np.float32)
-    with np.errstate(divide="ignore"):
-        invdeg = (np.float32(1.0) / deg).astype(np.float32)
-    return {"n_streams": n_streams, "tgt_bounds": bounds(tgt_rowptr), "src_bounds": bounds(src_rowptr),
-            "src_node": host["idxn"][perm].astype(np.int32), "src_tgt": src_tgt.astype(np.int32),
-            "src_invdeg": invdeg[src_tgt]}
-
-
-STREAM_MIN_EDGES = [200000]  # below this the graph is L2-resident and latency-bound: warp-per-node kernels
-
-
-def _stream_ok(x, w, graph, c):
-    return (w.dim() == 2 and c == 32 and x.dtype == torch.float32 and graph.idxe_host is None
-            and graph.n_edges >= STREAM_MIN_EDGES[0])
-
-
 # ------------------------------------------------------------------------------ ECC
 def ecc_fwd(x, w, graph, c_out, out=None):
     _need_cuda(x, w)
@@ -177,11 +136,6 @@ def ecc_fwd(x, w, graph, c_out, out=None):
         raise ValueError("weights has %d rows, graph needs %d" % (w.shape[0], n_w))
     if out is None:
         out = torch.empty((graph.n_out, c_out), dtype=x.dtype, device=x.device)
-    if _stream_ok(x, w, graph, c_in) and c_in == c_out and graph.n_in == graph.n_out:
-        st = graph.stream_arrays(x.device)
-        _lib.call("spg_ecc_vv_stream_fwd", x, w, g["tgt_rowptr"], st["tgt_bounds"], st["n_streams"],
-                  g["edge_tgt"], g["idxn"], out, graph.n_out, graph.n_edges, _lib.current_stream())
-        return out
     _lib.call("spg_ecc_fwd", x, w, g["tgt_rowptr"], g["idxn"], g["idxe"], out, graph.n_out,
               graph.n_edges, c_in, c_out, is_mat, _dt(x), _lib.current_stream())
     return out
@@ -216,12 +170,6 @@ def ecc_bwd_x(w, g_out, graph, c_in, add0=None, add1=None):
     is_mat = int(w.dim() == 3)
     c_out = g_out.shape[1]
     gx = torch.empty((graph.n_in, c_in), dtype=w.dtype, device=w.device)
-    if _stream_ok(g_out, w, graph, c_in) and c_in == c_out:
-        st = graph.stream_arrays(w.device)
-        _lib.call("spg_ecc_vv_stream_bwd_x", w, g_out, g["src_rowptr"], st["src_bounds"], st["n_streams"],
-                  st["src_node"], st["src_tgt"], g["src_perm"], st["src_invdeg"], add0, add1, gx,
-                  graph.n_in, graph.n_edges, _lib.current_stream())
-        return gx
     _lib.call("spg_ecc_bwd_x", w, g_out, g["tgt_rowptr"], g["src_rowptr"], g["src_perm"],
               g["edge_tgt"], g["idxe"], add0, add1, gx, graph.n_in, graph.n_edges, c_in, c_out,
               is_mat, _dt(w), _lib.current_stream())
@@ -479,18 +427,18 @@ def tc_dw_supported(M, co, ci, lddy, ldp):
             and bool(_lib.lib().spg_tc_dw_supported(int(M), int(co), int(ci))))
 
 
-def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None):
+def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None, centre=False):
     """dW[co,ci] = dY^T [co,M] f(P)[M,ci] on the tcgen05 3xTF32 kernel (ci may be the padded
     leading dimension of P; the caller slices the valid columns)."""
     _need_cuda(dY, P)
     dev = dY.device
     ctas = int(_lib.lib().spg_tc_dw_ctas(int(M)))
-    ws = workspace(ctas * co * ci, dev)
+    ws = workspace(ctas * co * ci + ci, dev)
     out = torch.empty((co, ci), dtype=torch.float32, device=dev)
     p_s, p_t, p_r = p_aff if p_aff is not None else (None, None, False)
     GEMM_FLOPS[0] += 2 * M * co * ci
     DW_FLOPS[0] += 2 * M * co * ci
-    _lib.call("spg_tc_dw", dY, lddy, P, ldp, p_s, p_t, int(bool(p_r)), out, ws, M, co, ci,
+    _lib.call("spg_tc_dw", dY, lddy, P, ldp, p_s, p_t, int(bool(p_r)), int(bool(centre)), out, ws, M, co, ci,
               _lib.current_stream())
     return out
 
@@ -749,3 +697,26 @@ def confusion_count(logits, label_mode, label_vec, confusion, counters, want_pre
     _lib.call("spg_confusion_count", logits, C, label_mode, label_vec, C, confusion, counters, pred,
               n, C, _lib.current_stream())
     return pred
+
+
+def labels_to_points(labels_red, comp_ptr, point_ids, n_ver):
+    _need_cuda(labels_red, comp_ptr, point_ids)
+    assert labels_red.dtype == torch.int64 and comp_ptr.dtype == torch.int64 and point_ids.dtype == torch.int64
+    out = torch.empty(n_ver, dtype=torch.uint8, device=labels_red.device)
+    _lib.call("spg_labels_to_points", _c(labels_red), _c(comp_ptr), _c(point_ids), comp_ptr.numel() - 1, out,
+              n_ver, _lib.current_stream())
+    return out
+
+
+def nn1_interpolate(xyz_ref, xyz_query, labels_ref=None, want_index=False):
+    """Exact 1-NN (float64 distances) of every query point among the reference points."""
+    _need_cuda(xyz_ref, xyz_query, labels_ref)
+    assert xyz_ref.dtype == torch.float32 and xyz_query.dtype == torch.float32
+    assert xyz_ref.shape[1] == 3 and xyz_query.shape[1] == 3
+    xyz_ref, xyz_query = _c(xyz_ref), _c(xyz_query)
+    m = xyz_query.shape[0]
+    lab = torch.empty(m, dtype=torch.int64, device=xyz_ref.device) if labels_ref is not None else None
+    idx = torch.empty(m, dtype=torch.int32, device=xyz_ref.device) if (want_index or labels_ref is None) else None
+    _lib.call("spg_nn1_interpolate", xyz_ref, xyz_ref.shape[0], xyz_query, m,
+              None if labels_ref is None else _c(labels_ref), lab, idx, _lib.current_stream())
+    return lab, idx

@@ -114,3 +114,42 @@ class MultiSampleMean(object):
         # tensor / tensor: IEEE division as numpy's true_divide (torch's CUDA tensor / python-scalar
         # multiplies by the reciprocal, which differs in the last bit)
         return self._sum / torch.full_like(self._sum, float(self._n))
+
+
+# ---- label up-sampling (the step after the metrics: predictions of the pruned cloud -> full cloud) ----
+def reduced_labels2full(labels_red, components, n_ver, device=None):
+    """labels of superpoints -> labels of their member points (ref: partition/provider.py:630-635).
+    `components`: list of index arrays (as read from the SPG file).  Returns a uint8 CUDA tensor."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    sizes = np.asarray([len(c) for c in components], dtype=np.int64)
+    ptr = np.zeros(len(components) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=ptr[1:])
+    ids = (np.concatenate([np.asarray(c, dtype=np.int64).reshape(-1) for c in components])
+           if len(components) else np.zeros(0, dtype=np.int64))
+    lab = torch.as_tensor(np.asarray(labels_red), dtype=torch.int64).reshape(-1).to(device)
+    return ops.labels_to_points(lab, torch.from_numpy(ptr).to(device), torch.from_numpy(ids).to(device), int(n_ver))
+
+
+def interpolate_labels(xyz_up, xyz, labels, ver_batch=0, return_index=False):
+    """Labels of the pruned cloud `xyz` [n,3] -> full cloud `xyz_up` [m,3] by exact 1-nearest
+    neighbour (ref: partition/provider.py:676-682; the reference's kd-tree works in float64 on the
+    float32 coordinates, and so does the kernel).  `labels` [n] or [n,C] (argmax taken, as the
+    reference does).  `ver_batch` > 0 processes the queries in slices of that many points
+    (provider.py:637-675 reads the full cloud in batches).  Returns int64 CUDA labels [m]."""
+    dev = xyz_up.device if torch.is_tensor(xyz_up) and xyz_up.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    ref = torch.as_tensor(xyz, dtype=torch.float32).to(dev).contiguous()
+    qry = torch.as_tensor(xyz_up, dtype=torch.float32).to(dev).contiguous()
+    lab = torch.as_tensor(labels).to(dev)
+    if lab.dim() > 1 and lab.shape[1] > 1:
+        lab = torch.argmax(lab, dim=1)
+    lab = lab.reshape(-1).to(torch.int64).contiguous()
+    step = int(ver_batch) if ver_batch and ver_batch > 0 else qry.shape[0]
+    outs, idxs = [], []
+    for i in range(0, qry.shape[0], max(step, 1)):
+        o, ix = ops.nn1_interpolate(ref, qry[i:i + step], lab, want_index=return_index)
+        outs.append(o)
+        idxs.append(ix)
+    out = torch.cat(outs) if outs else torch.zeros(0, dtype=torch.int64, device=dev)
+    if return_index:
+        return out, (torch.cat(idxs) if idxs else torch.zeros(0, dtype=torch.int32, device=dev))
+    return out

@@ -402,11 +402,48 @@ def metrics_confusion():
     save("metrics_confusion.npz", **out)
 
 
+def upsampling():
+    """partition/provider.py `interpolate_labels` / `reduced_labels2full`: the module as a whole does not
+    import under Python 3.12 (mixed tab/space indentation at provider.py:417, plyfile / libply_c absent), so
+    the SOURCE TEXT of the two functions is read from the reference checkout at generation time and executed
+    unmodified in a namespace holding what they use (numpy, scikit-learn's NearestNeighbors)."""
+    from sklearn.neighbors import NearestNeighbors
+    lines = open(os.path.join(REF, "partition", "provider.py")).read().split("\n")
+
+    def grab(name):
+        start = next(i for i, l in enumerate(lines) if l.startswith("def %s(" % name))
+        end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("#---") or lines[i].startswith("def "))
+        return "\n".join(lines[start:end])
+
+    ns = {"np": np, "NearestNeighbors": NearestNeighbors}
+    exec(grab("reduced_labels2full"), ns)
+    exec(grab("interpolate_labels"), ns)
+    provider = types.SimpleNamespace(**{k: ns[k] for k in ("reduced_labels2full", "interpolate_labels")})
+    rng = np.random.default_rng(23)
+    n, m = 700, 5000
+    xyz = rng.uniform(0, 10, size=(n, 3)).astype(np.float32)
+    xyz_up = np.concatenate([xyz + rng.normal(0, 0.05, size=xyz.shape).astype(np.float32),
+                             rng.uniform(-1, 11, size=(m - n, 3)).astype(np.float32)], 0)
+    logits = rng.standard_normal((n, 13)).astype(np.float32)
+    lab_up = provider.interpolate_labels(xyz_up, xyz, logits, 0)
+    hard = rng.integers(0, 13, size=n)
+    lab_up_hard = provider.interpolate_labels(xyz_up, xyz, hard, 0)
+    # superpoint labels -> points
+    comp_of = rng.integers(0, 40, size=n)
+    components = [np.nonzero(comp_of == c)[0] for c in range(40)]
+    labels_red = rng.integers(0, 13, size=40).astype(np.uint8)
+    full = provider.reduced_labels2full(labels_red, components, n)
+    save("upsampling.npz", xyz=xyz, xyz_up=xyz_up, logits=logits, lab_up=np.asarray(lab_up, dtype=np.int64),
+         hard=hard.astype(np.int64), lab_up_hard=np.asarray(lab_up_hard, dtype=np.int64), comp_of=comp_of.astype(np.int64),
+         labels_red=labels_red, full=full)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if sys.argv[1:] == ["loader"]:  # only the section-8(f) fixtures
         loader_clouds()
         metrics_confusion()
+        upsampling()
         sys.exit(0)
     ecc_unit_fixture()
     ecc_spg_shaped()
@@ -418,3 +455,4 @@ if __name__ == "__main__":
     train_steps()
     loader_clouds()
     metrics_confusion()
+    upsampling()

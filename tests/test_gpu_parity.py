@@ -170,38 +170,6 @@ def test_ecc_full_size_properties(dev):
 
 
 # ------------------------------------------------------------------------------------ GRU
-@pytest.mark.parametrize("heavy", [0, 3000])
-def test_ecc_stream_kernels_vs_oracle(dev, monkeypatch, heavy):
-    """Stream variants of the vector-filter kernels (runs of ~64 edge positions that end on segment
-    boundaries): forward and grad-input against the oracle, incl. zero-degree nodes at the ends and in
-    the middle, and one node whose degree exceeds a block's staging capacity (unstaged fallback)."""
-    from superpoint_graph_b200 import ops
-    monkeypatch.setattr(ops, "STREAM_MIN_EDGES", [0])
-    rng = np.random.default_rng(8)
-    N = 4000
-    degs = rng.integers(0, 21, size=N)
-    degs[[0, 1, 2, 777, 778, N - 1, N - 2]] = 0
-    if heavy:
-        degs[1500] = heavy
-    E = int(degs.sum())
-    idxn = rng.integers(0, N, size=E)
-    idxn[idxn == 5] = 6  # node 5 is nobody's source: an empty segment of the source-sorted order
-    graph = ops.EccGraph(t(idxn), None, t(degs), n_in=N)
-    x, w, g = torch.randn(N, 32), torch.randn(E, 32), torch.randn(N, 32)
-    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
-    ref = ecc_ref.graph_conv_forward(xr, wr, t(idxn), None, t(degs))
-    ref.backward(g)
-    out = ops.ecc_fwd(x.to(dev), w.to(dev), graph, 32)
-    close(out, ref, 1e-5, 1e-6)
-    assert torch.all(out[[0, 1, 2, 777, 778, N - 1, N - 2]] == 0)
-    a0, a1 = torch.randn(N, 32), torch.randn(N, 32)
-    gx = ops.ecc_bwd_x(w.to(dev), g.to(dev), graph, 32, add0=a0.to(dev), add1=a1.to(dev))
-    close(gx, xr.grad + a0 + a1, 1e-5, 1e-6)
-    close(ops.ecc_bwd_x(w.to(dev), g.to(dev), graph, 32), xr.grad, 1e-5, 1e-6)
-    st = graph.stream_arrays(dev)
-    assert st["n_streams"] == (E + 63) // 64
-
-
 @pytest.mark.parametrize("name,ln,ig", [("gru.npz", True, True), ("gru_plain.npz", False, False)])
 def test_gru_cell_golden(golden_dir, dev, name, ln, ig):
     from superpoint_graph_b200.spg_modules import GRUCellEx

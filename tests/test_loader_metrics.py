@@ -250,3 +250,45 @@ def test_cloud_build_unpadded_rows_take_the_scalar_path():
                     clouds, diam)
     assert np.array_equal(clouds.cpu().numpy(), g["s3dis_clouds"])
     assert np.array_equal(diam.cpu().numpy(), g["s3dis_global"])
+
+
+# ------------------------------------------------------------------ label up-sampling (8(f) rank 4)
+def test_oracle_upsampling_matches_reference_golden(golden_dir):
+    """oracle/loader_ref restatements against outputs of the reference's own function text
+    (partition/provider.py:630-635,676-682, generated by tests/golden/make_golden.py)."""
+    from oracle import loader_ref
+    g = np.load(os.path.join(golden_dir, "upsampling.npz"))
+    lab, _ = loader_ref.interpolate_labels(g["xyz_up"], g["xyz"], g["logits"])
+    assert np.array_equal(lab, g["lab_up"])
+    lab, _ = loader_ref.interpolate_labels(g["xyz_up"], g["xyz"], g["hard"])
+    assert np.array_equal(lab, g["lab_up_hard"])
+    comps = [np.nonzero(g["comp_of"] == c)[0] for c in range(40)]
+    assert np.array_equal(loader_ref.reduced_labels2full(g["labels_red"], comps, 700), g["full"])
+
+
+@pytest.mark.gpu
+def test_gpu_upsampling_bit_exact(golden_dir):
+    """spg_nn1_interpolate / spg_labels_to_points through the Python mirrors: labels identical to the
+    reference's (golden), neighbour indices identical to the oracle's, batched queries included; a
+    larger random case against the oracle."""
+    from oracle import loader_ref
+    from superpoint_graph_b200 import spg_metrics
+    g = np.load(os.path.join(golden_dir, "upsampling.npz"))
+    dev = torch.device("cuda:0")
+    lab, idx = spg_metrics.interpolate_labels(torch.from_numpy(g["xyz_up"]).to(dev), g["xyz"], g["logits"], return_index=True)
+    assert np.array_equal(lab.cpu().numpy(), g["lab_up"])
+    _, ref_idx = loader_ref.interpolate_labels(g["xyz_up"], g["xyz"], g["hard"])
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx)
+    lab_b = spg_metrics.interpolate_labels(g["xyz_up"], g["xyz"], g["hard"], ver_batch=777)
+    assert np.array_equal(lab_b.cpu().numpy(), g["lab_up_hard"])
+    comps = [np.nonzero(g["comp_of"] == c)[0] for c in range(40)]
+    full = spg_metrics.reduced_labels2full(g["labels_red"], comps, 700)
+    assert full.dtype == torch.uint8 and np.array_equal(full.cpu().numpy(), g["full"])
+    rng = np.random.default_rng(3)
+    xyz = rng.uniform(-50, 50, size=(3001, 3)).astype(np.float32)  # not a multiple of the 1024-point tile
+    up = rng.uniform(-55, 55, size=(20000, 3)).astype(np.float32)
+    labs = rng.integers(0, 8, size=3001)
+    want, want_idx = loader_ref.interpolate_labels(up, xyz, labs)
+    got, got_idx = spg_metrics.interpolate_labels(up, xyz, labs, return_index=True)
+    assert np.array_equal(got_idx.cpu().numpy().astype(np.int64), want_idx)
+    assert np.array_equal(got.cpu().numpy(), want)

@@ -31,7 +31,9 @@ def _run(tmp_path, cuda, extra=()):
     make_fixture.make(root, rooms_per_area=2, n_sp=60, seed=1)
     cmd = [sys.executable, os.path.join(ROOT, "compat", "run_main.py"), "--", "--dataset", "s3dis", "--S3DIS_PATH", root,
            "--cvfold", "5", "--epochs", "1", "--test_nth_epoch", "1", "--test_multisamp_n", "2", "--cuda", str(cuda),
-           "--odir", os.path.join(root, "out"), "--nworkers", "0", "--use_pyg", "0", "--batch_size", "2"] + list(extra)
+           "--odir", os.path.join(root, "out"), "--nworkers", "0", "--use_pyg", "0", "--batch_size", "2",
+           # S3DIS.md:27-30 (model for 13 classes; the script's defaults are Semantic3D's f_8)
+           "--model_config", "gru_10_1_1_1_0,f_13", "--ptn_nfeat_stn", "14", "--pc_attribs", "xyzrgbelpsvXYZ"] + list(extra)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=str(tmp_path))
     return root, out
 
