@@ -236,16 +236,13 @@ int spg_tc_gemm_ex(const float* A, int64_t lda, const float* weight_image, const
 /* Weight gradient of a point-wise layer on the tensor cores (3xTF32, fp32-equivalent):
  *   dW[co,ci] = sum_m dY[m,co] * f(P)[m,ci],  f = affine(p_scale,p_shift)+ReLU of P's producer.
  * co in {64,128,256}, ci in {32,64,128}; every CTA reduces a slab of points into a partial held in
- * TMEM, workspace >= spg_tc_dw_ctas(M)*co*ci + ci floats, partials are summed in a fixed order.
- * centre != 0 (only valid when sum_m dY[m,:] = 0, e.g. dY is the gradient w.r.t. the input of a
- * batch-statistics BatchNorm): f(P) is centred on column means estimated from the first 2048 points;
- * the result is mathematically unchanged, its rounding error is not amplified by M*mean(f(P)).
+ * TMEM, workspace >= spg_tc_dw_ctas(M)*co*ci floats, partials are summed in a fixed order.
  * C[M,N] = sum_z partials[z,M,N] (+ bias) is also exported on its own (spg_splitk_reduce).       */
 int spg_tc_dw_supported(int64_t M, int co, int ci);
 int spg_tc_dw_ctas(int64_t M);
 int spg_tc_dw(const float* dY, int64_t lddy, const float* P, int64_t ldp, const float* p_scale,
-              const float* p_shift, int p_relu, int centre, float* dW, float* workspace, int64_t M, int co,
-              int ci, spg_stream_t stream);
+              const float* p_shift, int p_relu, float* dW, float* workspace, int64_t M, int co, int ci,
+              spg_stream_t stream);
 int spg_splitk_reduce(const float* partials, int split, int64_t M, int64_t N, const float* bias,
                       float* C, int64_t ldc, spg_stream_t stream);
 
@@ -370,6 +367,22 @@ int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* l
                         const int64_t* label_vec, int64_t ld_vec, int64_t* confusion,
                         int64_t* counters, int64_t* pred_out, int64_t n_nodes, int n_classes,
                         spg_stream_t stream);
+/* Ragged superpoints (north_star: CSR offset array instead of the reference's resample-to-ptn_npts,
+ * learning/spg.py:209-214): point rows [P, ld] of all superpoints back to back, offsets int64 [B+1].
+ *   spg_segmax_csr_fwd: pooled[b,c] = max over the segment's rows of relu?(Y*scale+shift); argmax_row
+ *     int64 [B,C] = GLOBAL row of the first maximum (-1 and pooled 0 for an empty segment)
+ *   spg_segmax_csr_bwd: G[P,C] (zeroed here) receives g_pooled[b,c] at row argmax_row[b,c]
+ *   spg_rows_xy_transform(+_bwd): columns 0,1 of every row times its segment's 2x2 T (+I)
+ *     (learning/pointnet.py:123), row_seg int32 [P] = segment of each row; backward: dT [B,4].        */
+int spg_segmax_csr_fwd(const float* Y, int64_t ldy, const float* scale, const float* shift, int relu,
+                       const int64_t* offsets, float* pooled, int64_t ldp, int64_t* argmax_row, int64_t B,
+                       int C, spg_stream_t stream);
+int spg_segmax_csr_bwd(const float* g_pooled, int64_t ldg, const int64_t* argmax_row, float* G, int64_t ldG,
+                       int64_t B, int C, int64_t P, spg_stream_t stream);
+int spg_rows_xy_transform(const float* rows_in, const float* T, int add_eye, const int32_t* row_seg,
+                          float* rows_out, int64_t P, int64_t ld, spg_stream_t stream);
+int spg_rows_xy_transform_bwd(const float* rows_in, const float* d_rows_out, int64_t ld, const int64_t* offsets,
+                              float* dT, int64_t B, spg_stream_t stream);
 /* Label up-sampling, the step after the path (ref: partition/provider.py:630-635,676-682):
  * spg_labels_to_points: labels_full[n_ver] (uint8, zero-initialised here) gets labels_red[c] at every
  *   member point of component c; comp_ptr int64 [n_components+1] is the CSR over point_ids.

@@ -61,6 +61,32 @@ def pointnet_forward(x, x_global, sd, cfg, training, prefix=''):
     return fc_stack(x, sd, prefix + 'fcs.', cfg['n_fc'], training, last_ac=False)
 
 
+def pointnet_forward_ragged(points, offsets, x_global, sd, cfg, training, prefix=''):
+    """PointNet.forward (learning/pointnet.py:120-133) WITHOUT the loader's resample-to-ptn_npts
+    (spg.py:209-214): `points` [P,F] of all superpoints back to back, `offsets` [B+1].  The 1x1 convolutions
+    and their BatchNorm see all points at once ([1,F,P]: BatchNorm1d reduces over batch and length alike),
+    every max-pool runs over one superpoint's own points.  No reference counterpart exists for unequal
+    segment lengths (parity unpinned there); with equal lengths it IS pointnet_forward (tested)."""
+    B = len(offsets) - 1
+    x = points.t().unsqueeze(0)                                             # [1,F,P]
+
+    def segmax(y):                                                          # [1,C,P] -> [B,C]
+        return torch.stack([y[0, :, int(offsets[b]):int(offsets[b + 1])].max(1)[0] for b in range(B)])
+
+    if cfg['nfeat_stn'] > 0:
+        h = conv_stack(x[:, :cfg['nfeat_stn'], :], sd, prefix + 'stn.convs.', cfg['n_conv_stn'], training)
+        h = fc_stack(segmax(h), sd, prefix + 'stn.fcs.', cfg['n_fc_stn'], training, last_ac=True)
+        T = F.linear(h, sd[prefix + 'stn.proj.weight'], sd[prefix + 'stn.proj.bias']).view(-1, 2, 2)
+        T = T + torch.eye(2, dtype=T.dtype).unsqueeze(0)
+        seg = torch.repeat_interleave(torch.arange(B), torch.as_tensor(offsets[1:]) - torch.as_tensor(offsets[:-1]))
+        xy = torch.bmm(points[:, None, :2], T[seg]).squeeze(1)              # row vector times T (:123)
+        x = torch.cat([xy, points[:, 2:]], 1).t().unsqueeze(0)
+    h = segmax(conv_stack(x, sd, prefix + 'convs.', cfg['n_conv'], training))
+    if x_global is not None:
+        h = torch.cat([h, x_global.view(B, -1)], 1)
+    return fc_stack(h, sd, prefix + 'fcs.', cfg['n_fc'], training, last_ac=False)
+
+
 def cloud_embed(clouds, clouds_global, clouds_flag, sd, cfg, training, prefix=''):
     """CloudEmbedder.run_full, learning/pointnet.py:147-158: PointNet on the valid clouds,
     scattered into zero descriptors."""

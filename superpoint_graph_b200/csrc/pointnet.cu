@@ -310,6 +310,113 @@ __global__ void rows_gather_kernel(const float* __restrict__ src, const int64_t*
     dst[i] = src[idx[r] * C + (i % C)];
 }
 
+// ------------------------------------------------------------------ ragged (CSR) segments
+// north_star: "ragged segment boundaries carried as a CSR offset array and reduced by warp-shuffle
+// segmented max".  The reference never feeds ragged clouds (its loader resamples every superpoint to
+// ptn_npts points, spg.py:209-214); these kernels are the variant WITHOUT that resampling: point rows
+// [P, ld] of all superpoints back to back, offsets int64 [B+1].  A warp owns (segment, 32 channels):
+// lane = channel for coalesced 128-byte row reads, the segment's rows are strided over the 8 warps of
+// the block and folded through shared memory; ties keep the FIRST maximum (as max_pool1d).
+// argmax is the GLOBAL row index (int64), -1 for an empty segment (pooled value 0).
+__global__ void __launch_bounds__(256)
+segmax_csr_fwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
+                      const float* __restrict__ shift, int relu, const int64_t* __restrict__ offsets,
+                      float* __restrict__ pooled, int64_t ldp, int64_t* __restrict__ argmax, int C) {
+    __shared__ float s_v[8][32];
+    __shared__ long long s_i[8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
+    const int64_t b = blockIdx.y;
+    const int64_t r0 = offsets[b], r1 = offsets[b + 1];
+    float best = -FLT_MAX;
+    long long bi = -1;
+    if (c < C) {
+        const float sc = scale ? scale[c] : 1.f, sh = shift ? shift[c] : 0.f;
+        for (int64_t r = r0 + y; r < r1; r += 8) {
+            float v = fmaf(__ldg(Y + r * ldy + c), sc, sh);
+            if (relu) v = fmaxf(v, 0.f);
+            if (bi < 0 || v > best) {
+                best = v;
+                bi = r;
+            }
+        }
+    }
+    s_v[y][x] = best;
+    s_i[y][x] = bi;
+    __syncthreads();
+    if (y == 0 && c < C) {
+        for (int j = 1; j < 8; ++j) {
+            const float v = s_v[j][x];
+            const long long i = s_i[j][x];
+            if (i >= 0 && (bi < 0 || v > best || (v == best && i < bi))) {
+                best = v;
+                bi = i;
+            }
+        }
+        pooled[b * ldp + c] = bi >= 0 ? best : 0.f;
+        argmax[b * C + c] = bi;
+    }
+}
+
+// G[P, C] = 0 except G[argmax[b,c], c] = g_pooled[b, c]   (G is zeroed by the launcher)
+__global__ void __launch_bounds__(256)
+segmax_csr_bwd_kernel(const float* __restrict__ gp, int64_t ldg, const int64_t* __restrict__ argmax,
+                      float* __restrict__ G, int64_t ldG, int64_t B, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int64_t b = i / C;
+    const int c = (int)(i % C);
+    const int64_t r = argmax[i];
+    if (r >= 0) G[r * ldG + c] = gp[b * ldg + c];
+}
+
+// rows_out = rows_in with columns 0,1 replaced by (x0,x1) * (T[seg] (+ I))   (pointnet.py:123)
+__global__ void __launch_bounds__(256)
+rows_xy_transform_kernel(const float* __restrict__ in, const float* __restrict__ T, int add_eye,
+                         const int32_t* __restrict__ row_seg, float* __restrict__ out, int64_t P,
+                         int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * ld) return;
+    const int64_t r = i / ld;
+    const int f = (int)(i % ld);
+    float v = in[i];
+    if (f < 2) {
+        const int64_t b = row_seg[r];
+        const float eye = add_eye ? 1.f : 0.f;
+        const float x0 = in[r * ld], x1 = in[r * ld + 1];
+        v = f == 0 ? fmaf(x0, T[b * 4 + 0] + eye, x1 * T[b * 4 + 2])
+                   : fmaf(x0, T[b * 4 + 1], x1 * (T[b * 4 + 3] + eye));
+    }
+    out[i] = v;
+}
+
+// dT[b] = sum over the rows of segment b of (x0, x1)^T (d0, d1); one warp per segment.
+__global__ void __launch_bounds__(256)
+rows_xy_transform_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dOut, int64_t ld,
+                             const int64_t* __restrict__ offsets, float* __restrict__ dT, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    for (int64_t r = offsets[b] + lane; r < offsets[b + 1]; r += 32) {
+        const float x0 = in[r * ld], x1 = in[r * ld + 1], d0 = dOut[r * ld], d1 = dOut[r * ld + 1];
+        a00 = fmaf(x0, d0, a00);
+        a01 = fmaf(x0, d1, a01);
+        a10 = fmaf(x1, d0, a10);
+        a11 = fmaf(x1, d1, a11);
+    }
+    a00 = warp_sum(a00);
+    a01 = warp_sum(a01);
+    a10 = warp_sum(a10);
+    a11 = warp_sum(a11);
+    if (lane == 0) {
+        dT[b * 4 + 0] = a00;
+        dT[b * 4 + 1] = a01;
+        dT[b * 4 + 2] = a10;
+        dT[b * 4 + 3] = a11;
+    }
+}
+
 }  // namespace spg
 
 using namespace spg;
@@ -436,6 +543,53 @@ int spg_rows_gather(const float* src, const int64_t* idx, float* dst, int64_t n_
     if (!src || !idx || !dst) return SPG_E_BADARG;
     SPG_LAUNCH(K_ROWS_GATHER, (cudaStream_t)stream, rows_gather_kernel,
                (unsigned)ceil_div64(n_dst * C, 256), 256, 0, src, idx, dst, n_dst, C);
+    return launch_status();
+}
+
+int spg_segmax_csr_fwd(const float* Y, int64_t ldy, const float* scale, const float* shift, int relu,
+                       const int64_t* offsets, float* pooled, int64_t ldp, int64_t* argmax_row, int64_t B,
+                       int C, spg_stream_t stream) {
+    if (B < 0 || C <= 0 || ldy < C || ldp < C) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!Y || !offsets || !pooled || !argmax_row) return SPG_E_BADARG;
+    if (B > 65535) return SPG_E_UNSUPPORTED;  // grid.y
+    dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)B);
+    SPG_LAUNCH(K_SEGMAX_FWD, (cudaStream_t)stream, segmax_csr_fwd_kernel, grid, 256, 0, Y, ldy, scale, shift,
+               relu, offsets, pooled, ldp, (int64_t*)argmax_row, C);
+    return launch_status();
+}
+
+int spg_segmax_csr_bwd(const float* g_pooled, int64_t ldg, const int64_t* argmax_row, float* G, int64_t ldG,
+                       int64_t B, int C, int64_t P, spg_stream_t stream) {
+    if (B < 0 || C <= 0 || P < 0 || ldG < C || ldg < C) return SPG_E_BADARG;
+    if (P == 0) return SPG_OK;
+    if (!G) return SPG_E_BADARG;
+    cudaError_t e = cudaMemsetAsync(G, 0, (size_t)P * ldG * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    if (B == 0) return SPG_OK;
+    if (!g_pooled || !argmax_row) return SPG_E_BADARG;
+    SPG_LAUNCH(K_SEGMAX_BWD, (cudaStream_t)stream, segmax_csr_bwd_kernel, (unsigned)ceil_div64(B * C, 256), 256,
+               0, g_pooled, ldg, argmax_row, G, ldG, B, C);
+    return launch_status();
+}
+
+int spg_rows_xy_transform(const float* rows_in, const float* T, int add_eye, const int32_t* row_seg,
+                          float* rows_out, int64_t P, int64_t ld, spg_stream_t stream) {
+    if (P < 0 || ld < 2) return SPG_E_BADARG;
+    if (P == 0) return SPG_OK;
+    if (!rows_in || !T || !row_seg || !rows_out) return SPG_E_BADARG;
+    SPG_LAUNCH(K_CLOUD_ROWS, (cudaStream_t)stream, rows_xy_transform_kernel, (unsigned)ceil_div64(P * ld, 256),
+               256, 0, rows_in, T, add_eye, row_seg, rows_out, P, ld);
+    return launch_status();
+}
+
+int spg_rows_xy_transform_bwd(const float* rows_in, const float* d_rows_out, int64_t ld, const int64_t* offsets,
+                              float* dT, int64_t B, spg_stream_t stream) {
+    if (B < 0 || ld < 2) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!rows_in || !d_rows_out || !offsets || !dT) return SPG_E_BADARG;
+    SPG_LAUNCH(K_STN_APPLY_BWD, (cudaStream_t)stream, rows_xy_transform_bwd_kernel,
+               (unsigned)ceil_div64(B * 32, 256), 256, 0, rows_in, d_rows_out, ld, offsets, dT, B);
     return launch_status();
 }
 

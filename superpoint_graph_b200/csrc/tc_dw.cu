@@ -28,7 +28,6 @@ struct DwArgs {
     int64_t ldp;
     const float *p_scale, *p_shift;
     int p_relu;
-    const float* p_center;  // optional per-column constant subtracted from f(P) (see spg_tc_dw)
     float* partial;  // [gridDim.x, CO, CI]
     int64_t M;
     int64_t pts_per_cta;  // multiple of DW_PTS
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
     const int64_t m_end = min(p.M, m_beg + p.pts_per_cta);
     const int nchunks = m_beg < m_end ? (int)((m_end - m_beg + DW_PTS - 1) / DW_PTS) : 0;
     constexpr uint32_t idesc = umma_idesc_tf32_major(128, CI, 1, 1);
-    const bool pro = p.p_scale || p.p_shift || p.p_relu || p.p_center;
+    const bool pro = p.p_scale || p.p_shift || p.p_relu;
 
     float4 ra[A_F4], rb[B_F4];
     auto load_chunk = [&](int ch) {
@@ -164,13 +163,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
                     v.y = fmaxf(v.y, 0.f);
                     v.z = fmaxf(v.z, 0.f);
                     v.w = fmaxf(v.w, 0.f);
-                }
-                if (p.p_center) {
-                    const float4 mu = __ldg(reinterpret_cast<const float4*>(p.p_center + c4 * 4));
-                    v.x -= mu.x;
-                    v.y -= mu.y;
-                    v.z -= mu.z;
-                    v.w -= mu.w;
                 }
             }
             split_store(b_hi, b_lo, mn_off<MB_B>(pt, c4), v);
@@ -253,33 +245,6 @@ static int launch_dw(const DwArgs& a, int ctas, cudaStream_t s) {
     return launch_status();
 }
 
-// Column means of f(P) over the first `rows` points (f = affine + ReLU as in tc_dw): the centre that
-// spg_tc_dw subtracts when the caller knows that sum_m dY[m,:] = 0.
-__global__ void __launch_bounds__(256)
-act_colmean_kernel(const float* __restrict__ P, int64_t ldp, const float* __restrict__ sc,
-                   const float* __restrict__ sh, int relu, int rows, int C, float* __restrict__ mu) {
-    __shared__ float part[8][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
-    float a = 0.f;
-    if (c < C) {
-        const float s = sc ? sc[c] : 1.f, t = sh ? sh[c] : 0.f;
-        for (int r = warp; r < rows; r += 8) {
-            float v = fmaf(__ldg(P + (int64_t)r * ldp + c), s, t);
-            if (relu) v = fmaxf(v, 0.f);
-            a += v;
-        }
-    }
-    part[warp][lane] = a;
-    __syncthreads();
-    if (warp == 0 && c < C) {
-        float tsum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tsum += part[j][lane];
-        mu[c] = tsum / (float)rows;
-    }
-}
-
 }  // namespace spg
 
 using namespace spg;
@@ -299,8 +264,8 @@ int spg_tc_dw_ctas(int64_t M) {
 }
 
 int spg_tc_dw(const float* dY, int64_t lddy, const float* P, int64_t ldp, const float* p_scale,
-              const float* p_shift, int p_relu, int centre, float* dW, float* workspace, int64_t M, int co,
-              int ci, spg_stream_t stream) {
+              const float* p_shift, int p_relu, float* dW, float* workspace, int64_t M, int co, int ci,
+              spg_stream_t stream) {
     if (!dY || !P || !dW || !workspace || M <= 0) return SPG_E_BADARG;
     if (!spg_tc_dw_supported(M, co, ci)) return SPG_E_UNSUPPORTED;
     if ((lddy & 3) || (ldp & 3) || lddy < co || ldp < ci) return SPG_E_ALIGN;
@@ -310,20 +275,7 @@ int spg_tc_dw(const float* dY, int64_t lddy, const float* P, int64_t ldp, const 
     DwArgs a;
     a.dY = dY; a.lddy = lddy; a.P = P; a.ldp = ldp; a.p_scale = p_scale; a.p_shift = p_shift;
     a.p_relu = p_relu; a.partial = workspace; a.M = M;
-    a.p_center = nullptr;
     cudaStream_t s = (cudaStream_t)stream;
-    if (centre) {
-        // dW = sum_m dY[m,:]^T (f(P)[m,:] - mu) is exact for ANY mu when sum_m dY[m,:] = 0; with mu close
-        // to the column means the products are zero-mean and the rounding error of the (computed, not
-        // exactly zero) column sums of dY no longer gets multiplied by M * mean(f(P))
-        float* mu = workspace + (size_t)ctas * co * ci;
-        const int rows = (int)(M < 2048 ? M : 2048);
-        SPG_LAUNCH(K_COLSUM_PARTIAL, s, act_colmean_kernel, (unsigned)ceil_div64(ci, 32), 256, 0, P, ldp, p_scale,
-                   p_shift, p_relu, rows, ci, mu);
-        int rc0 = launch_status();
-        if (rc0) return rc0;
-        a.p_center = mu;
-    }
     a.pts_per_cta = ceil_div64(ceil_div64(M, ctas), DW_PTS) * DW_PTS;
     int rc;
 #define SPG_DW_CASE(CO_, CI_) \

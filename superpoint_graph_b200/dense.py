@@ -230,9 +230,7 @@ def chain_backward(G, ldg, M, specs, params, saved, need_input_grad, grads, own_
         def weight_grads(dY, ldy, cur=cur, nxt=nxt, mean=mean, sp=sp, Wp=Wp, C=C):
             kpad = _padded_k(sp.cin, cur.ld)
             if ops.tc_dw_supported(M, sp.cout, kpad, ldy, cur.ld) and (kpad == sp.cin or not cur.pending):
-                # the column sums of dY vanish behind a batch-statistics BatchNorm: centred operand
-                dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, kpad, p_aff=cur.aff(),
-                               centre=(sp.bn is not None and mean is not None))
+                dW = ops.tc_dw(dY, ldy, cur.raw, cur.ld, M, sp.cout, kpad, p_aff=cur.aff())
                 if kpad != sp.cin:
                     dW = dW[:, :sp.cin].contiguous()
             else:

@@ -427,18 +427,18 @@ def tc_dw_supported(M, co, ci, lddy, ldp):
             and bool(_lib.lib().spg_tc_dw_supported(int(M), int(co), int(ci))))
 
 
-def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None, centre=False):
+def tc_dw(dY, lddy, P, ldp, M, co, ci, p_aff=None):
     """dW[co,ci] = dY^T [co,M] f(P)[M,ci] on the tcgen05 3xTF32 kernel (ci may be the padded
     leading dimension of P; the caller slices the valid columns)."""
     _need_cuda(dY, P)
     dev = dY.device
     ctas = int(_lib.lib().spg_tc_dw_ctas(int(M)))
-    ws = workspace(ctas * co * ci + ci, dev)
+    ws = workspace(ctas * co * ci, dev)
     out = torch.empty((co, ci), dtype=torch.float32, device=dev)
     p_s, p_t, p_r = p_aff if p_aff is not None else (None, None, False)
     GEMM_FLOPS[0] += 2 * M * co * ci
     DW_FLOPS[0] += 2 * M * co * ci
-    _lib.call("spg_tc_dw", dY, lddy, P, ldp, p_s, p_t, int(bool(p_r)), int(bool(centre)), out, ws, M, co, ci,
+    _lib.call("spg_tc_dw", dY, lddy, P, ldp, p_s, p_t, int(bool(p_r)), out, ws, M, co, ci,
               _lib.current_stream())
     return out
 
@@ -720,3 +720,38 @@ def nn1_interpolate(xyz_ref, xyz_query, labels_ref=None, want_index=False):
     _lib.call("spg_nn1_interpolate", xyz_ref, xyz_ref.shape[0], xyz_query, m,
               None if labels_ref is None else _c(labels_ref), lab, idx, _lib.current_stream())
     return lab, idx
+
+
+# ------------------------------------------------------------------ ragged (CSR) superpoints
+def segmax_csr_fwd(Y, ldy, offsets, C, scale, shift, relu, pooled, ldp):
+    _need_cuda(Y, offsets, pooled)
+    assert offsets.dtype == torch.int64 and offsets.is_contiguous()
+    B = offsets.numel() - 1
+    argmax = torch.empty((B, C), dtype=torch.int64, device=Y.device)
+    _lib.call("spg_segmax_csr_fwd", Y, ldy, scale, shift, int(bool(relu)), offsets, pooled, ldp, argmax, B, C,
+              _lib.current_stream())
+    return argmax
+
+
+def segmax_csr_bwd(g_pooled, ldg, argmax, P, C):
+    _need_cuda(g_pooled, argmax)
+    G = torch.empty((P, C), dtype=torch.float32, device=g_pooled.device)
+    _lib.call("spg_segmax_csr_bwd", g_pooled, ldg, argmax, G, C, argmax.shape[0], C, P, _lib.current_stream())
+    return G
+
+
+def rows_xy_transform(rows, T, row_seg, add_eye=True):
+    _need_cuda(rows, T, row_seg)
+    assert rows.is_contiguous() and row_seg.dtype == torch.int32
+    out = torch.empty_like(rows)
+    _lib.call("spg_rows_xy_transform", rows, _c(T), int(bool(add_eye)), row_seg, out, rows.shape[0], rows.shape[1],
+              _lib.current_stream())
+    return out
+
+
+def rows_xy_transform_bwd(rows, d_out, offsets):
+    _need_cuda(rows, d_out, offsets)
+    B = offsets.numel() - 1
+    dT = torch.empty((B, 4), dtype=torch.float32, device=rows.device)
+    _lib.call("spg_rows_xy_transform_bwd", rows, _c(d_out), rows.shape[1], offsets, dT, B, _lib.current_stream())
+    return dT

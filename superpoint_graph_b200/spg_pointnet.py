@@ -210,6 +210,22 @@ class PointNet(nn.Module):
                                        training, *params)
 
 
+    def forward_ragged(self, points, offsets, input_global):
+        """Ragged superpoints (north_star; no counterpart in the reference, whose loader resamples every
+        superpoint to ptn_npts points, spg.py:209-214): `points` [P, nfeat] float32 holds the points of all
+        B superpoints back to back, `offsets` int64 [B+1] is the CSR boundary array, `input_global` [B] |
+        [B,G] | None.  Same network, same parameters, same BatchNorm semantics (statistics over all P
+        points); the max-pool runs over each superpoint's own points.  With equal-length segments the
+        result equals `forward` on the [B, nfeat, L] layout."""
+        training = self.training
+        stn_g, conv_g, fc_g, params = self._groups(training)
+        B = offsets.numel() - 1
+        if input_global is not None:
+            input_global = input_global.reshape(B, -1).float()
+        return _PointNetRaggedFunction.apply(points, offsets, input_global, self.nfeat_stn,
+                                             (stn_g, conv_g, fc_g), training, *params)
+
+
 def prepack_weights(ptn, n_clouds, n_points, extra=()):
     """One launch that builds every tensor-core weight image the next training forward+backward of
     `ptn` on [n_clouds, F, n_points] will use (called by the Trainer at the start of a step).
@@ -294,6 +310,82 @@ class _PointNetFunction(torch.autograd.Function):
         ctx.saved = None
         ctx.clouds = None
         return (None, None, None, None, None) + tuple(grads)
+
+
+class _PointNetRaggedFunction(torch.autograd.Function):
+    """PointNet over CSR segments: the dense chains of _PointNetFunction with segmax_csr_* /
+    rows_xy_transform* in place of the constant-L kernels."""
+
+    @staticmethod
+    def forward(ctx, points, offsets, glob, nfeat_stn, groups, training, *params):
+        stn_g, conv_g, fc_g = groups
+        if points.dtype != torch.float32 or points.dim() != 2:
+            raise TypeError("ragged PointNet input must be float32 [P, nfeat]")
+        offsets = offsets.to(torch.int64).contiguous()
+        P, F = points.shape
+        B = offsets.numel() - 1
+        ld = _row_ld(F)
+        rows0 = torch.empty((P, ld), dtype=torch.float32, device=points.device)
+        ops.zero_(rows0)
+        ops.affine_act(points.contiguous(), F, P, F, out=rows0, ldo=ld)
+        row_seg = torch.repeat_interleave(torch.arange(B, device=points.device, dtype=torch.int32),
+                                          (offsets[1:] - offsets[:-1]))
+        saved = {} if training else None
+        T = None
+        rows = rows0
+        if nfeat_stn > 0:
+            cs, fs = stn_g
+            sv_c = [] if training else None
+            o = chain_forward(Deferred(rows0, ld, cs[0].cin), P, cs, params, training, sv_c)
+            Cs = o.C
+            pooled_s = torch.empty((B, Cs), dtype=torch.float32, device=points.device)
+            am_s = ops.segmax_csr_fwd(o.raw, o.ld, offsets, Cs, o.scale, o.shift, o.relu, pooled_s, Cs)
+            sv_f = [] if training else None
+            t = chain_forward(Deferred(pooled_s, Cs, Cs), B, fs, params, training, sv_f)
+            T = t.materialise(B)
+            rows = ops.rows_xy_transform(rows0, T, row_seg, add_eye=True)
+            if training:
+                saved.update(stn_c=sv_c, stn_f=sv_f, stn_am=am_s, stn_Cs=Cs)
+        sv_c = [] if training else None
+        out = chain_forward(Deferred(rows, ld, F), P, conv_g, params, training, sv_c)
+        Ct = out.C
+        G = 0 if glob is None else glob.shape[1]
+        ldp = _round4(Ct + G)
+        pooled = torch.empty((B, ldp), dtype=torch.float32, device=points.device)
+        am = ops.segmax_csr_fwd(out.raw, out.ld, offsets, Ct, out.scale, out.shift, out.relu, pooled, ldp)
+        if G > 0:
+            ops.affine_act(glob.contiguous(), G, B, G, out=pooled[:, Ct:], ldo=ldp)
+        sv_f = [] if training else None
+        y = chain_forward(Deferred(pooled, ldp, Ct + G), B, fc_g, params, training, sv_f)
+        res = y.materialise(B)
+        if training:
+            saved.update(conv=sv_c, fc=sv_f, am=am, Ct=Ct)
+        ctx.saved, ctx.groups, ctx.params = saved, groups, params
+        ctx.dims = (B, P, nfeat_stn)
+        ctx.aux = (offsets, rows0) if (training and nfeat_stn > 0) else None
+        return res
+
+    @staticmethod
+    def backward(ctx, gy):
+        if ctx.saved is None:
+            raise RuntimeError("backward through an eval-mode forward is not supported")
+        stn_g, conv_g, fc_g = ctx.groups
+        params, saved = ctx.params, ctx.saved
+        B, P, nfeat_stn = ctx.dims
+        grads = [None] * len(params)
+        Ct = saved["Ct"]
+        g_pool = chain_backward(gy.contiguous(), gy.shape[1], B, fc_g, params, saved["fc"], True, grads)
+        G = ops.segmax_csr_bwd(g_pool, g_pool.shape[1], saved["am"], P, Ct)
+        g_rows = chain_backward(G, Ct, P, conv_g, params, saved["conv"], nfeat_stn > 0, grads, own_g=True)
+        if nfeat_stn > 0:
+            offsets, rows0 = ctx.aux
+            cs, fs = stn_g
+            dT = ops.rows_xy_transform_bwd(rows0, g_rows, offsets)
+            g_ps = chain_backward(dT, 4, B, fs, params, saved["stn_f"], True, grads)
+            Gs = ops.segmax_csr_bwd(g_ps, g_ps.shape[1], saved["stn_am"], P, saved["stn_Cs"])
+            chain_backward(Gs, saved["stn_Cs"], P, cs, params, saved["stn_c"], False, grads, own_g=True)
+        ctx.saved = ctx.aux = None
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 class CloudEmbedder():

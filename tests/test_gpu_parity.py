@@ -370,6 +370,53 @@ def test_pointnet_small_golden(golden_dir, dev):
         close(net.stn(x[:, :cfg["nfeat_stn"]].contiguous()), g["T_eval"])
 
 
+def test_pointnet_ragged_csr(golden_dir, dev):
+    """PointNet.forward_ragged (CSR offset array, no resample-to-ptn_npts): (1) with equal segment lengths
+    it reproduces the reference's golden outputs and gradients; (2) with unequal lengths (1..300 points)
+    it matches the oracle's ragged restatement, forward and backward, S3DIS widths."""
+    from superpoint_graph_b200.spg_pointnet import PointNet
+    g = load(golden_dir, "pointnet_small.npz")
+    cfg = json.loads(str(g["cfg"]))
+    net = PointNet(cfg["nf_conv"], cfg["nf_fc"], cfg["nf_conv_stn"], cfg["nf_fc_stn"], cfg["nfeat"],
+                   cfg["nfeat_stn"], prelast_do=0)
+    net.load_state_dict(sub(g, "sd0."))
+    net.to(dev).train()
+    x, xg = t(g["x"]), t(g["xg"], dev)
+    B, F, L = x.shape
+    pts = x.permute(0, 2, 1).reshape(B * L, F).contiguous().to(dev)
+    offs = (torch.arange(B + 1) * L).to(dev)
+    out = net.forward_ragged(pts, offs, xg)
+    close(out, g["out_train"])
+    out.backward(t(g["g"], dev))
+    close_grads({k: p.grad for k, p in net.named_parameters()}, sub(g, "grad."), 3e-4)
+    net.eval()
+    with torch.no_grad():
+        close(net.forward_ragged(pts, offs, xg), g["out_eval"])
+    # (2) unequal lengths, S3DIS widths
+    torch.manual_seed(6)
+    net = PointNet([64, 64, 128, 128, 256], [256, 64, 32], [64, 64, 128], [128, 64], 14, 14, prelast_do=0)
+    with torch.no_grad():
+        net.stn.proj.weight.normal_(0, 0.05)
+    sd = {k: v.clone().requires_grad_(nets_ref.is_param(k)) for k, v in net.state_dict().items()}
+    rng = np.random.default_rng(6)
+    lens = rng.integers(1, 301, size=97)
+    lens[[3, 50]] = 1
+    offsets = np.concatenate([[0], np.cumsum(lens)])
+    P = int(offsets[-1])
+    points = torch.randn(P, 14) * 0.4
+    glob = torch.rand(97) * 3
+    pcfg = dict(n_conv=5, n_fc=3, n_conv_stn=3, n_fc_stn=2, nfeat_stn=14)
+    ref = nets_ref.pointnet_forward_ragged(points, offsets, glob, sd, pcfg, True)
+    gy = torch.randn(97, 32)
+    ref.backward(gy)
+    net.to(dev).train()
+    out = net.forward_ragged(points.to(dev), torch.from_numpy(offsets).to(dev), glob.to(dev))
+    close(out, ref)
+    out.backward(gy.to(dev))
+    close_grads({k: p.grad for k, p in net.named_parameters()},
+                {k: v.grad for k, v in sd.items() if v.requires_grad}, 1e-3)
+
+
 def test_pointnet_s3dis_widths_vs_oracle(dev):
     """The S3DIS architecture (main.py:104-107) at L=128, training-mode forward+backward."""
     from superpoint_graph_b200.spg_pointnet import PointNet

@@ -199,3 +199,23 @@ def test_two_training_steps(golden_dir):
                 # first steps move it by +-lr per step whatever the noise's sign is
                 noise_driven = k == "0._fnet.4.bias"
                 close(tr.sd_ecc[k].detach(), v, 5e-3, 2.1e-2 if noise_driven else 1e-5)
+
+
+def test_ragged_pointnet_oracle_equals_reference_for_equal_lengths(golden_dir):
+    """oracle.nets_ref.pointnet_forward_ragged (CSR segments, no resampling) reproduces the reference's
+    PointNet outputs when every superpoint has the same number of points (pointnet_small.npz: train-mode
+    and eval-mode outputs) — the pin of the ragged restatement."""
+    import json
+    g = np.load(os.path.join(golden_dir, "pointnet_small.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    sd = {k[len("sd0."):]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("sd0.")}
+    pcfg = dict(n_conv=len(cfg["nf_conv"]), n_fc=len(cfg["nf_fc"]), n_conv_stn=len(cfg["nf_conv_stn"]),
+                n_fc_stn=len(cfg["nf_fc_stn"]), nfeat_stn=cfg["nfeat_stn"])
+    x, xg = torch.from_numpy(g["x"]), torch.from_numpy(g["xg"])
+    B, F, L = x.shape
+    points = x.permute(0, 2, 1).reshape(B * L, F)
+    offsets = np.arange(B + 1) * L
+    out = nets_ref.pointnet_forward_ragged(points, offsets, xg, sd, pcfg, True)  # updates the running statistics
+    assert float((out - torch.from_numpy(g["out_train"])).abs().max()) <= 1e-5 * float(np.abs(g["out_train"]).max())
+    out = nets_ref.pointnet_forward_ragged(points, offsets, xg, sd, pcfg, False)  # eval after that one update (as the golden)
+    assert float((out - torch.from_numpy(g["out_eval"])).abs().max()) <= 1e-5 * float(np.abs(g["out_eval"]).max())
