@@ -192,6 +192,9 @@ int spg_colstats_merge_fold(float* partials, int64_t n_partials, int C, float* m
 int64_t spg_tc_weight_image_floats(int N, int K);
 int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K, int k_valid,
                         float* image, spg_stream_t stream);
+/* image of diag(row_scale) * W (W = [N,K], ld ldw): eval-mode BatchNorm folded into the weights */
+int spg_tc_pack_weights_scaled(const float* W, int64_t ldw, const float* row_scale, int N, int K, int k_valid,
+                               float* image, spg_stream_t stream);
 /* All weight images of a model in one launch: table (device, int64 [n_jobs,8]) rows are
  * {W, ldw, transpose, N, K, k_valid, image, first element index}; total = sum N*K.            */
 int spg_tc_pack_weights_multi(const int64_t* table, int n_jobs, int64_t total, spg_stream_t stream);
@@ -367,6 +370,22 @@ int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* l
                         const int64_t* label_vec, int64_t ld_vec, int64_t* confusion,
                         int64_t* counters, int64_t* pred_out, int64_t n_nodes, int n_classes,
                         spg_stream_t stream);
+/* Eval-mode PointNet trunk, fully fused (ref: learning/pointnet.py:55-61,120-127 under model.eval()):
+ * for every superpoint b (n_points must be 128 = one tensor-core M tile, n_features <= 16):
+ *   x = clouds[b] ([F, 128], NCL as the reference stacks them, learning/spg.py:162)
+ *   if T: (x0, x1) <- (x0, x1) (T[b] (+ I))                                   (pointnet.py:123)
+ *   for l < n_layers: x <- relu(W_l x + b_l)     W_l [widths[l], K_l], BatchNorm already folded in
+ *   pooled[b, :widths[n_layers-1]] = max over the 128 points
+ * Activations stay in shared memory / TMEM; the input tile and the weight stream arrive by TMA;
+ * products are 3xTF32 on tcgen05 (fp32-equivalent).  weight_image = for each layer the
+ * spg_tc_pack_weights_scaled image ([K_l/32][hi|lo][N_l][32 floats]; K_0 = 32, k_valid = F) back to
+ * back (spg_pointnet_fused_image_rows(...) * 32 floats); bias = the folded biases back to back;
+ * widths: HOST int32 array, every width in {64,128,256}, inner widths <= 128, at most 6 layers.     */
+int spg_pointnet_fused_supported(int n_features, int n_points, int n_layers, const int32_t* widths);
+int64_t spg_pointnet_fused_image_rows(int n_features, int n_layers, const int32_t* widths);
+int spg_pointnet_fused_eval(const float* clouds, int64_t n_clouds, int n_features, int n_points, const float* T,
+                            int add_eye, const float* weight_image, const float* bias, int n_layers,
+                            const int32_t* widths, float* pooled, int64_t ldp, spg_stream_t stream);
 /* Ragged superpoints (north_star: CSR offset array instead of the reference's resample-to-ptn_npts,
  * learning/spg.py:209-214): point rows [P, ld] of all superpoints back to back, offsets int64 [B+1].
  *   spg_segmax_csr_fwd: pooled[b,c] = max over the segment's rows of relu?(Y*scale+shift); argmax_row

@@ -48,6 +48,7 @@ enum KernelId {
     K_CLOUD_BUILD,
     K_CONFUSION,
     K_TC_MERGE,
+    K_POINTNET_FUSED,
     K_COUNT
 };
 

@@ -30,6 +30,25 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int64_t ldw,
     img[base + (int64_t)N * TC_KC + off] = __uint_as_float(lo);
 }
 
+// Same image from W[n][k] * row_scale[n]: eval-mode BatchNorm folded into the weights
+// (scale = gamma / sqrt(running_var + eps)); consumed by pointnet_fused.cu.
+__global__ void tc_pack_weights_scaled_kernel(const float* __restrict__ W, int64_t ldw,
+                                              const float* __restrict__ row_scale, int N, int K, int k_valid,
+                                              float* __restrict__ img) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int n = (int)(i / K), k = (int)(i % K);
+    float v = 0.f;
+    if (k < k_valid) v = W[(int64_t)n * ldw + k] * (row_scale ? row_scale[n] : 1.f);
+    const uint32_t hi = to_tf32(v);
+    const uint32_t lo = to_tf32(v - __uint_as_float(hi));
+    const int kc = k / TC_KC, kk = k % TC_KC;
+    const int64_t base = (int64_t)kc * 2 * N * TC_KC;
+    const int64_t off = (int64_t)(sw128_off(n, kk >> 2) >> 2) + (kk & 3);
+    img[base + off] = __uint_as_float(hi);
+    img[base + (int64_t)N * TC_KC + off] = __uint_as_float(lo);
+}
+
 // Batched variant: one launch packs every weight matrix of a model (forward images and the
 // transposed images of the data-gradient GEMMs).  table[j] = {W, ldw, transpose, N, K, k_valid,
 // image, first element index of job j}; a thread finds its job by a linear scan (<= 64 jobs).
@@ -72,6 +91,16 @@ int spg_tc_pack_weights(const float* W, int64_t ldw, int transpose, int N, int K
     const int64_t total = (int64_t)N * K;
     SPG_LAUNCH(K_TC_PACK, (cudaStream_t)stream, tc_pack_weights_kernel,
                (unsigned)ceil_div64(total, 256), 256, 0, W, ldw, transpose, N, K, k_valid, image);
+    return launch_status();
+}
+
+int spg_tc_pack_weights_scaled(const float* W, int64_t ldw, const float* row_scale, int N, int K, int k_valid,
+                               float* image, spg_stream_t stream) {
+    if (!W || !image || N <= 0 || K <= 0 || k_valid <= 0 || k_valid > K) return SPG_E_BADARG;
+    if (K % TC_KC != 0 || N % 8 != 0) return SPG_E_UNSUPPORTED;
+    const int64_t total = (int64_t)N * K;
+    SPG_LAUNCH(K_TC_PACK, (cudaStream_t)stream, tc_pack_weights_scaled_kernel,
+               (unsigned)ceil_div64(total, 256), 256, 0, W, ldw, row_scale, N, K, k_valid, image);
     return launch_status();
 }
 

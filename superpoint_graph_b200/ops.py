@@ -305,6 +305,7 @@ def gemm(A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias=None, out=None, ldc=N
 USE_TC = [os.environ.get("SPG_TC", "1") != "0"]  # tcgen05 path for the large point-wise layers
 USE_FUSED_RNN = [os.environ.get("SPG_FUSED_RNN", "1") != "0"]  # one-kernel R x {ECC, cell} loop
 USE_FUSED_BNBWD = [os.environ.get("SPG_FUSED_BNBWD", "1") != "0"]  # BatchNorm backward inside the dX GEMM (prologue + epilogue sums)
+USE_FUSED_EVAL = [os.environ.get("SPG_FUSED_EVAL", "1") != "0"]  # eval-mode PointNet trunk as one kernel per chain
 USE_SIDE_STREAM = [os.environ.get("SPG_SIDE_STREAM", "1") != "0"]  # Trainer: block-local weight gradients on a 2nd stream
 
 
@@ -755,3 +756,62 @@ def rows_xy_transform_bwd(rows, d_out, offsets):
     dT = torch.empty((B, 4), dtype=torch.float32, device=rows.device)
     _lib.call("spg_rows_xy_transform_bwd", rows, _c(d_out), rows.shape[1], offsets, dT, B, _lib.current_stream())
     return dT
+
+
+# ------------------------------------------------------------------ fused eval-mode PointNet trunk
+def pointnet_fused_supported(F, L, widths):
+    w = torch.tensor(list(widths), dtype=torch.int32)
+    return USE_FUSED_EVAL[0] and bool(_lib.lib().spg_pointnet_fused_supported(int(F), int(L), len(widths), w.data_ptr()))
+
+
+_FUSED_IMAGES = {}  # parameter versions -> (weight image, folded bias, widths tensor)
+
+
+def pointnet_fused_image(layers, F):
+    """layers: [(W [N,K] (2-D view), bias|None, bn_module|None)] of a Conv1d(k=1)+BatchNorm+ReLU chain in eval
+    mode.  Returns (image, bias, widths): BatchNorm folded into weights and bias (scale = gamma/sqrt(rv+eps),
+    bias' = bias*scale + beta - rm*scale), packed for spg_pointnet_fused_eval.  Cached on the tensors'
+    version counters (eval weights do not change between batches)."""
+    key = []
+    for W, b, bn in layers:
+        ts = [W, b] + ([bn.running_mean, bn.running_var, bn.weight, bn.bias] if bn is not None else [])
+        key += [(x.data_ptr(), x._version) for x in ts if x is not None]
+    key = (int(F),) + tuple(key)
+    ent = _FUSED_IMAGES.get(key)
+    if ent is not None:
+        return ent
+    dev = layers[0][0].device
+    widths = torch.tensor([int(W.shape[0]) for W, _, _ in layers], dtype=torch.int32)
+    rows = int(_lib.lib().spg_pointnet_fused_image_rows(int(F), len(layers), widths.data_ptr()))
+    image = torch.empty(rows * 32, dtype=torch.float32, device=dev)
+    bias = torch.empty(int(widths.sum()), dtype=torch.float32, device=dev)
+    row, boff, K = 0, 0, 32
+    for W, b, bn in layers:
+        N, kv = int(W.shape[0]), int(W.shape[1])
+        scale = shift = None
+        if bn is not None:
+            scale, shift = bn_fold(bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps)
+        _lib.call("spg_tc_pack_weights_scaled", W, W.stride(0), scale, N, K, kv, image[row * 32:], _lib.current_stream())
+        bsl = bias[boff:boff + N]
+        if b is not None:
+            affine_act(b.detach().reshape(1, N), N, 1, N, scale, shift, False, out=bsl, ldo=N)
+        elif shift is not None:
+            bsl.copy_(shift)
+        else:
+            zero_(bsl)
+        row += (K // 32) * 2 * N
+        boff += N
+        K = N
+    if len(_FUSED_IMAGES) > 64:
+        _FUSED_IMAGES.clear()
+    _FUSED_IMAGES[key] = (image, bias, widths)
+    return image, bias, widths
+
+
+def pointnet_fused_eval(clouds, T, image, bias, widths, pooled, ldp):
+    """pooled[b, :widths[-1]] = max over points of the folded conv chain on clouds[b] (xy transformed by T+I)."""
+    _need_cuda(clouds, image, bias, pooled, T)
+    B, F, L = clouds.shape
+    _lib.call("spg_pointnet_fused_eval", clouds, B, F, L, None if T is None else _c(T), 1, image, bias,
+              int(widths.numel()), widths.data_ptr(), pooled, ldp, _lib.current_stream())
+    return pooled

@@ -258,6 +258,9 @@ class _PointNetFunction(torch.autograd.Function):
         B, F, L = clouds.shape
         M = B * L
         ld = _row_ld(F)
+        if not training and _fused_eval_ok(groups, params, F, L, nfeat_stn):
+            ctx.saved = None
+            return _fused_eval_forward(clouds, glob, nfeat_stn, groups, params)
         saved = {} if training else None
         T = None
         if nfeat_stn > 0:
@@ -310,6 +313,57 @@ class _PointNetFunction(torch.autograd.Function):
         ctx.saved = None
         ctx.clouds = None
         return (None, None, None, None, None) + tuple(grads)
+
+
+def _conv_layers(specs, params):
+    """[(W2d, bias, bn)] of a parsed Conv1d(k=1)+BatchNorm+ReLU chain, or None if it is not of that form."""
+    out = []
+    for sp in specs:
+        if sp.bn is None or not sp.relu or not sp.bn.track_running_stats or sp.bn.running_mean is None:
+            return None
+        W = params[sp.w]
+        W = W.view(W.shape[0], W.shape[1]) if W.dim() == 3 else W
+        out.append((W, params[sp.b] if sp.b is not None else None, sp.bn))
+    return out
+
+
+def _fused_eval_ok(groups, params, F, L, nfeat_stn):
+    stn_g, conv_g, fc_g = groups
+    if not conv_g or _conv_layers(conv_g, params) is None:
+        return False
+    if not ops.pointnet_fused_supported(F, L, [sp.cout for sp in conv_g]):
+        return False
+    if nfeat_stn > 0:
+        if nfeat_stn != F or _conv_layers(stn_g[0], params) is None:
+            return False
+        if not ops.pointnet_fused_supported(F, L, [sp.cout for sp in stn_g[0]]):
+            return False
+    return True
+
+
+def _fused_eval_forward(clouds, glob, nfeat_stn, groups, params):
+    """Eval-mode PointNet with both point-wise chains fused (ops.pointnet_fused_eval: input tile to pooled row
+    on chip); only the [B, C] pooled rows and the small FC chains touch HBM.  ref: pointnet.py:120-133."""
+    stn_g, conv_g, fc_g = groups
+    B, F, L = clouds.shape
+    dev = clouds.device
+    T = None
+    if nfeat_stn > 0:
+        cs, fs = stn_g
+        img, bias, widths = ops.pointnet_fused_image(_conv_layers(cs, params), F)
+        Cs = cs[-1].cout
+        pooled_s = torch.empty((B, Cs), dtype=torch.float32, device=dev)
+        ops.pointnet_fused_eval(clouds, None, img, bias, widths, pooled_s, Cs)
+        T = chain_forward(Deferred(pooled_s, Cs, Cs), B, fs, params, False, None).materialise(B)
+    img, bias, widths = ops.pointnet_fused_image(_conv_layers(conv_g, params), F)
+    Ct = conv_g[-1].cout
+    G = 0 if glob is None else glob.shape[1]
+    ldp = _round4(Ct + G)
+    pooled = torch.empty((B, ldp), dtype=torch.float32, device=dev)
+    ops.pointnet_fused_eval(clouds, T, img, bias, widths, pooled, ldp)
+    if G > 0:
+        ops.affine_act(glob.contiguous(), G, B, G, out=pooled[:, Ct:], ldo=ldp)
+    return chain_forward(Deferred(pooled, ldp, Ct + G), B, fc_g, params, False, None).materialise(B)
 
 
 class _PointNetRaggedFunction(torch.autograd.Function):

@@ -588,6 +588,38 @@ def test_eval_chunking_matches_unchunked(dev, monkeypatch):
     assert torch.equal(whole, sliced)
 
 
+@pytest.mark.parametrize("F,B", [(14, 301), (11, 64), (9, 1)])
+def test_fused_eval_trunk_vs_oracle(dev, monkeypatch, F, B):
+    """Eval-mode PointNet with both point-wise chains fused into one kernel each (input tile -> STN chain /
+    xy transform + 5 layers -> max-pool, BatchNorm folded, activations never in HBM) against the oracle
+    and against the layer-by-layer path; the fused kernel must actually be the one that ran."""
+    from superpoint_graph_b200 import ops, spg_pointnet
+    net = spg_pointnet.PointNet([64, 64, 128, 128, 256], [256, 64, 32], [64, 64, 128], [128, 64], F, F, prelast_do=0)
+    torch.manual_seed(3 + F)
+    with torch.no_grad():
+        net.stn.proj.weight.normal_(0, 0.05)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x, xg = torch.randn(B, F, 128) * 0.4, torch.rand(B) * 3
+    pcfg = dict(n_conv=5, n_fc=3, n_conv_stn=3, n_fc_stn=2, nfeat_stn=F)
+    ref = nets_ref.pointnet_forward(x, xg, sd, pcfg, False)
+    net.to(dev).eval()
+    ops.prof_reset()
+    with torch.no_grad():
+        fused = net(x.to(dev), xg.to(dev))
+        assert ops.prof_collect().get("pointnet_fused_eval", (0, 0))[0] == 2  # STN chain + main chain
+        monkeypatch.setattr(ops, "USE_FUSED_EVAL", [False])
+        layered = net(x.to(dev), xg.to(dev))
+    close(fused, ref)
+    close(layered, ref)
+    close(fused, layered, 2e-5)
+
+
 def test_local_cloud_embedder_tiny_clouds(dev):
     """Learned-partition embedder (configs[3] first half, pointnet.py:182-207): external STN on 2
     features, 20-point clouds, global features + flattened T, L2-normalised 4-D output."""
