@@ -400,8 +400,8 @@ int spg_segmax_csr_bwd(const float* g_pooled, int64_t ldg, const int64_t* argmax
                        int64_t B, int C, int64_t P, spg_stream_t stream);
 int spg_rows_xy_transform(const float* rows_in, const float* T, int add_eye, const int32_t* row_seg,
                           float* rows_out, int64_t P, int64_t ld, spg_stream_t stream);
-int spg_rows_xy_transform_bwd(const float* rows_in, const float* d_rows_out, int64_t ld, const int64_t* offsets,
-                              float* dT, int64_t B, spg_stream_t stream);
+int spg_rows_xy_transform_bwd(const float* rows_in, int64_t ld, const float* d_rows_out, int64_t ld_d,
+                              const int64_t* offsets, float* dT, int64_t B, spg_stream_t stream);
 /* Label up-sampling, the step after the path (ref: partition/provider.py:630-635,676-682):
  * spg_labels_to_points: labels_full[n_ver] (uint8, zero-initialised here) gets labels_red[c] at every
  *   member point of component c; comp_ptr int64 [n_components+1] is the CSR over point_ids.

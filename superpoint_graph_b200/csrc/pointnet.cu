@@ -392,14 +392,15 @@ rows_xy_transform_kernel(const float* __restrict__ in, const float* __restrict__
 
 // dT[b] = sum over the rows of segment b of (x0, x1)^T (d0, d1); one warp per segment.
 __global__ void __launch_bounds__(256)
-rows_xy_transform_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dOut, int64_t ld,
-                             const int64_t* __restrict__ offsets, float* __restrict__ dT, int64_t B) {
+rows_xy_transform_bwd_kernel(const float* __restrict__ in, int64_t ld, const float* __restrict__ dOut,
+                             int64_t ldd, const int64_t* __restrict__ offsets, float* __restrict__ dT,
+                             int64_t B) {
     const int lane = threadIdx.x & 31;
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;
     float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
     for (int64_t r = offsets[b] + lane; r < offsets[b + 1]; r += 32) {
-        const float x0 = in[r * ld], x1 = in[r * ld + 1], d0 = dOut[r * ld], d1 = dOut[r * ld + 1];
+        const float x0 = in[r * ld], x1 = in[r * ld + 1], d0 = dOut[r * ldd], d1 = dOut[r * ldd + 1];
         a00 = fmaf(x0, d0, a00);
         a01 = fmaf(x0, d1, a01);
         a10 = fmaf(x1, d0, a10);
@@ -583,13 +584,13 @@ int spg_rows_xy_transform(const float* rows_in, const float* T, int add_eye, con
     return launch_status();
 }
 
-int spg_rows_xy_transform_bwd(const float* rows_in, const float* d_rows_out, int64_t ld, const int64_t* offsets,
-                              float* dT, int64_t B, spg_stream_t stream) {
-    if (B < 0 || ld < 2) return SPG_E_BADARG;
+int spg_rows_xy_transform_bwd(const float* rows_in, int64_t ld, const float* d_rows_out, int64_t ld_d,
+                              const int64_t* offsets, float* dT, int64_t B, spg_stream_t stream) {
+    if (B < 0 || ld < 2 || ld_d < 2) return SPG_E_BADARG;
     if (B == 0) return SPG_OK;
     if (!rows_in || !d_rows_out || !offsets || !dT) return SPG_E_BADARG;
     SPG_LAUNCH(K_STN_APPLY_BWD, (cudaStream_t)stream, rows_xy_transform_bwd_kernel,
-               (unsigned)ceil_div64(B * 32, 256), 256, 0, rows_in, d_rows_out, ld, offsets, dT, B);
+               (unsigned)ceil_div64(B * 32, 256), 256, 0, rows_in, ld, d_rows_out, ld_d, offsets, dT, B);
     return launch_status();
 }
 

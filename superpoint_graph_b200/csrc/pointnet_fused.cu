@@ -8,20 +8,21 @@
 //   F.max_pool1d over the points.
 //
 // Per CTA (persistent over superpoints b = blockIdx.x, blockIdx.x + gridDim.x, ...):
-//   warp 4 (one thread)  TMA producer: the superpoint's [F, 128] input tile (cp.async.bulk.tensor over the
+//   warp 8 (one thread)  TMA producer: the superpoint's [F, 128] input tile (cp.async.bulk.tensor over the
 //                        NCL clouds tensor) and the weight stream — for every layer, N-tile and 32-float
 //                        K-chunk one [N_tile x 128 B] hi block and one lo block of the pre-split,
 //                        pre-swizzled weight image (the weights live in L2; 2-stage ring of 32 KB)
-//   warp 5 (one thread)  MMA issuer: tcgen05.mma kind::tf32, 3 MMAs per product (3xTF32: fp32-equivalent),
+//   warp 9 (one thread)  MMA issuer: tcgen05.mma kind::tf32, 3 MMAs per product (3xTF32: fp32-equivalent),
 //                        A = the layer's input activations in shared memory (K-major SWIZZLE_128B hi/lo),
 //                        B = the weight stage, D = TMEM accumulator (one 128-column tile per N-tile)
-//   warps 0-3            one thread per point: input tile -> transform -> tf32 split -> A; after every
+//   warps 0-7            one thread per (point, half of the channel blocks): input tile -> transform -> tf32 split -> A; after every
 //                        layer tcgen05.ld of the accumulator row, + folded bias, ReLU, tf32 split, written
 //                        IN PLACE as the next layer's A operand; after the last layer the max over the 128
 //                        points (redux.sync on the non-negative float bits) -> pooled[b, :]
 // mbarriers: w_full/w_empty (weight ring), x_full/x_empty (input double buffer), a_ready (A operand of the
 // next layer is in shared memory), acc_full[t] (all MMAs of N-tile t have completed).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -33,15 +34,20 @@ namespace spg {
 constexpr int PF_ROWS = 128;          // points per superpoint = UMMA M
 constexpr int PF_KC = 32;             // floats per K chunk (one 128-byte swizzle row)
 constexpr int PF_MAXK = 128;          // widest layer input kept in shared memory
-constexpr int PF_NT = 128;            // accumulator tile width (TMEM columns per N-tile)
-constexpr int PF_STAGES = 2;
-constexpr int PF_STAGE_BYTES = 2 * PF_NT * PF_KC * 4;        // hi + lo = 32 KB
+constexpr int PF_NT = 128;            // accumulator tile width (TMEM columns per N-tile).  (64-column tiles would let
+                                      // the activation warps drain tile t under the MMAs of tile t+1, but the next A
+                                      // operand is written IN PLACE: every MMA of the layer must have finished first)
+constexpr int PF_MAX_TILES = 2;
+constexpr int PF_STAGES_SMEM_A = 2;   // weight ring depth (32 KB stages) next to a 128 KB shared-memory A operand
+constexpr int PF_STAGES_TMEM_A = 6;   // ... and when the A operand lives in tensor memory
+constexpr int PF_STAGE_BYTES = 2 * PF_NT * PF_KC * 4;        // hi + lo of one (N-tile, K-chunk) = 32 KB
 constexpr int PF_A_CHUNK_BYTES = 2 * PF_ROWS * PF_KC * 4;    // hi + lo of one K chunk = 32 KB
 constexpr int PF_A_BYTES = (PF_MAXK / PF_KC) * PF_A_CHUNK_BYTES;  // 128 KB
 constexpr int PF_MAXF = 16;            // input features (S3DIS 14, Semantic3D 11, vKITTI 9)
 constexpr int PF_X_BYTES = PF_MAXF * PF_ROWS * 4;            // one input tile buffer (8 KB)
 constexpr int PF_MAX_LAYERS = 6;
-constexpr int PF_THREADS = 192;
+constexpr int PF_ACT_WARPS = 8;        // activation warps: two per TMEM lane quarter (alternate 32-column blocks)
+constexpr int PF_THREADS = (PF_ACT_WARPS + 2) * 32;
 constexpr int PF_MAX_BIAS = 1024;
 
 struct PfLayer {
@@ -90,18 +96,51 @@ __device__ __forceinline__ void pf_split_store(uint32_t a_hi, int row, int c16, 
                  "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
 }
 
+// A operand from tensor memory (lane = row, one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// ATM = true: the A operand (the layer's input activations, tf32 hi | lo) lives in TENSOR MEMORY: the
+// activation warps write the row they own with tcgen05.st (TMEM lane = point, column = channel — the
+// layout the accumulator row already has, no shared-memory transposition), the MMA reads it directly,
+// and all of shared memory goes to a 6-stage weight ring.  TMEM columns: [0,256) accumulators,
+// [256,384) A hi, [384,512) A lo.  ATM = false keeps A in shared memory (K-major SWIZZLE_128B).
+template <bool ATM>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                       const __grid_constant__ CUtensorMap xmap) {
+    constexpr int PF_STAGES = ATM ? PF_STAGES_TMEM_A : PF_STAGES_SMEM_A;
+    constexpr uint32_t TM_COLS = ATM ? 512u : 256u;
+    constexpr uint32_t TM_AHI = 256u, TM_ALO = 384u;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
-    // [A operand 128 KB][weight ring 2 x 32 KB][input tiles 2 x 8 KB][bias][pool scratch]
+    // [A operand 128 KB (shared-memory variant only)][weight ring][input tiles 2 x 8 KB][bias][pool scratch]
     uint8_t* a_s = smem;
-    uint8_t* w_s = a_s + PF_A_BYTES;
+    uint8_t* w_s = a_s + (ATM ? 0 : PF_A_BYTES);
     uint8_t* x_s = w_s + PF_STAGES * PF_STAGE_BYTES;
     float* bias_s = reinterpret_cast<float*>(x_s + 2 * PF_X_BYTES);
     float* pool_s = bias_s + PF_MAX_BIAS;  // [4 warps][256]
-    __shared__ __align__(8) uint64_t bars[2 * PF_STAGES + 4 + 1 + 2];
+    __shared__ __align__(8) uint64_t bars[2 * PF_STAGES_TMEM_A + 4 + 1 + PF_MAX_TILES];
     __shared__ uint32_t tmem_base_s;
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -120,16 +159,16 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(x_full(s), 1);
-            mbar_init(x_empty(s), 4);
-            mbar_init(acc_full(s), 1);
+            mbar_init(x_empty(s), PF_ACT_WARPS);
         }
-        mbar_init(a_ready, 4);
+        for (int s = 0; s < PF_MAX_TILES; ++s) mbar_init(acc_full(s), 1);
+        mbar_init(a_ready, PF_ACT_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+                         smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = t; i < p.n_bias; i += PF_THREADS) bias_s[i] = p.bias[i];
@@ -139,7 +178,7 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t a_u = smem_u32(a_s), w_u = smem_u32(w_s), x_u = smem_u32(x_s);
 
-    if (warp == 4) {
+    if (warp == PF_ACT_WARPS) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
@@ -168,7 +207,7 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == PF_ACT_WARPS + 1) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             uint32_t it = 0, q = 0;
@@ -192,11 +231,19 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
 #pragma unroll
                             for (int ks = 0; ks < PF_KC / 8; ++ks) {
                                 const uint32_t ko = ks * 32;
-                                const uint64_t dah = umma_desc_k_sw128(a_hi + ko), dal = umma_desc_k_sw128(a_lo + ko);
                                 const uint64_t dbh = umma_desc_k_sw128(b_hi + ko), dbl = umma_desc_k_sw128(b_lo + ko);
-                                umma_tf32(d, dah, dbh, idesc, (kc | ks) ? 1u : 0u);
-                                umma_tf32(d, dal, dbh, idesc, 1u);
-                                umma_tf32(d, dah, dbl, idesc, 1u);
+                                if (ATM) {
+                                    const uint32_t th = tmem_base + TM_AHI + (uint32_t)(kc * PF_KC + ks * 8);
+                                    const uint32_t tl = tmem_base + TM_ALO + (uint32_t)(kc * PF_KC + ks * 8);
+                                    umma_tf32_ts(d, th, dbh, idesc, (kc | ks) ? 1u : 0u);
+                                    umma_tf32_ts(d, tl, dbh, idesc, 1u);
+                                    umma_tf32_ts(d, th, dbl, idesc, 1u);
+                                } else {
+                                    const uint64_t dah = umma_desc_k_sw128(a_hi + ko), dal = umma_desc_k_sw128(a_lo + ko);
+                                    umma_tf32(d, dah, dbh, idesc, (kc | ks) ? 1u : 0u);
+                                    umma_tf32(d, dal, dbh, idesc, 1u);
+                                    umma_tf32(d, dah, dbl, idesc, 1u);
+                                }
                             }
                             umma_commit(w_empty(s));
                         }
@@ -207,8 +254,9 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
         }
     } else {
         // ======================= activation warps: one thread per point =======================
-        const int row = t;  // 0..127 = TMEM lane = point of the superpoint
-        uint32_t ci = 0, acc_cnt[2] = {0u, 0u};
+        const int quarter = warp & 3, half = warp >> 2;  // TMEM lane quarter; which 32-column blocks
+        const int row = quarter * 32 + lane;             // 0..127 = TMEM lane = point of the superpoint
+        uint32_t ci = 0, acc_cnt[PF_MAX_TILES] = {0u, 0u};
         for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++ci) {
             // ---- input tile -> (xy transform) -> A chunk 0
             const int xb = ci & 1;
@@ -227,12 +275,37 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                 v[0] = fmaf(x0, t00, x1 * t10);  // row vector times T (pointnet.py:123)
                 v[1] = fmaf(x0, t01, x1 * t11);
             }
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            auto store_chunk = [&](int kc, const float (&o)[32]) {
+                // 32 consecutive channels of this thread's row = K chunk kc of the next A operand
+                if (ATM) {
+                    uint32_t hi[32], lo[32];
 #pragma unroll
-            for (int c16 = 0; c16 < 8; ++c16)
-                pf_split_store(a_u, row, c16, make_float4(v[4 * c16], v[4 * c16 + 1], v[4 * c16 + 2], v[4 * c16 + 3]));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) pf_arrive(a_ready);
+                    for (int j = 0; j < 32; ++j) {
+                        hi[j] = to_tf32(o[j]);
+                        lo[j] = to_tf32(o[j] - __uint_as_float(hi[j]));
+                    }
+                    tmem_st32(lane_base + TM_AHI + (uint32_t)(kc * PF_KC), hi);
+                    tmem_st32(lane_base + TM_ALO + (uint32_t)(kc * PF_KC), lo);
+                } else {
+                    const uint32_t a_hi = a_u + (uint32_t)kc * PF_A_CHUNK_BYTES;
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16)
+                        pf_split_store(a_hi, row, c16, make_float4(o[4 * c16], o[4 * c16 + 1], o[4 * c16 + 2], o[4 * c16 + 3]));
+                }
+            };
+            auto publish_a = [&]() {
+                if (ATM) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) pf_arrive(a_ready);
+            };
+            if (half == 0) store_chunk(0, v);
+            publish_a();
             // ---- layers
             for (int l = 0; l < p.n_layers; ++l) {
                 const PfLayer& Ly = p.L[l];
@@ -242,23 +315,17 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                     mbar_wait(acc_full(nt), acc_cnt[nt] & 1);
                     ++acc_cnt[nt];
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int cb = 0; cb < ntile / 32; ++cb) {
+                    for (int cb = half; cb < ntile / 32; cb += PF_ACT_WARPS / 4) {
                         uint32_t r[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(nt * PF_NT + cb * 32), r);
+                        tmem_ld32(lane_base + (uint32_t)(nt * PF_NT + cb * 32), r);
                         const int col0 = nt * ntile + cb * 32;
                         const float* bs = bias_s + Ly.b_off + col0;
                         if (!last) {
                             // next layer's A operand: these 32 columns are exactly K chunk col0/32
-                            const uint32_t a_hi = a_u + (uint32_t)(col0 / PF_KC) * PF_A_CHUNK_BYTES;
+                            float o[32];
 #pragma unroll
-                            for (int c16 = 0; c16 < 8; ++c16) {
-                                float4 o;
-                                o.x = fmaxf(__uint_as_float(r[4 * c16]) + bs[4 * c16], 0.f);
-                                o.y = fmaxf(__uint_as_float(r[4 * c16 + 1]) + bs[4 * c16 + 1], 0.f);
-                                o.z = fmaxf(__uint_as_float(r[4 * c16 + 2]) + bs[4 * c16 + 2], 0.f);
-                                o.w = fmaxf(__uint_as_float(r[4 * c16 + 3]) + bs[4 * c16 + 3], 0.f);
-                                pf_split_store(a_hi, row, c16, o);
-                            }
+                            for (int j = 0; j < 32; ++j) o[j] = fmaxf(__uint_as_float(r[j]) + bs[j], 0.f);
+                            store_chunk(col0 / PF_KC, o);
                         } else {
                             // max over the 32 points of this warp: ReLU output is >= 0, so the float order
                             // is the unsigned order of the bit patterns (one redux.sync per column)
@@ -266,25 +333,22 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                             for (int j = 0; j < 32; ++j) {
                                 const float o = fmaxf(__uint_as_float(r[j]) + bs[j], 0.f);
                                 const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(o));
-                                if (lane == j) pool_s[warp * 256 + col0 + j] = __uint_as_float(m);
+                                if (lane == j) pool_s[quarter * 256 + col0 + j] = __uint_as_float(m);
                             }
                         }
                     }
                 }
                 if (!last) {
                     // (all MMAs that read the old A have completed: acc_full of every N-tile was waited for)
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) pf_arrive(a_ready);
+                    publish_a();
                 } else {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    for (int c = t; c < Ly.N; c += 128) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(PF_ACT_WARPS * 32) : "memory");
+                    for (int c = t; c < Ly.N; c += PF_ACT_WARPS * 32) {
                         const float m = fmaxf(fmaxf(pool_s[c], pool_s[256 + c]), fmaxf(pool_s[512 + c], pool_s[768 + c]));
                         p.pooled[b * p.ldp + c] = m;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(PF_ACT_WARPS * 32) : "memory");
                 }
             }
         }
@@ -294,7 +358,7 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TM_COLS) : "memory");
     }
 }
 
@@ -387,12 +451,26 @@ int spg_pointnet_fused_eval(const float* clouds, int64_t n_clouds, int n_feature
     if (rc) return rc;
     rc = pf_map_2d(&xmap, clouds, PF_ROWS, (uint64_t)(n_clouds * n_features), PF_ROWS, (uint32_t)n_features);
     if (rc) return rc;
-    const int smem = PF_A_BYTES + PF_STAGES * PF_STAGE_BYTES + 2 * PF_X_BYTES + (PF_MAX_BIAS + 4 * 256) * 4;
-    cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
+    static int a_in_tmem = -1;
+    if (a_in_tmem < 0) {
+        const char* env = getenv("SPG_FUSED_A_TMEM");
+        a_in_tmem = env ? atoi(env) : 1;
+    }
     const int64_t grid = n_clouds < kNumSMs ? n_clouds : kNumSMs;
-    SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel, (unsigned)grid, PF_THREADS, smem, a,
-               wmap, xmap);
+    const int tail = 2 * PF_X_BYTES + (PF_MAX_BIAS + 4 * 256) * 4;
+    if (a_in_tmem) {
+        const int smem = PF_STAGES_TMEM_A * PF_STAGE_BYTES + tail;
+        cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel<true>, (unsigned)grid, PF_THREADS,
+                   smem, a, wmap, xmap);
+    } else {
+        const int smem = PF_A_BYTES + PF_STAGES_SMEM_A * PF_STAGE_BYTES + tail;
+        cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel<false>, (unsigned)grid, PF_THREADS,
+                   smem, a, wmap, xmap);
+    }
     return launch_status();
 }
 

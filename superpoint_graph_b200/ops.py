@@ -754,7 +754,9 @@ def rows_xy_transform_bwd(rows, d_out, offsets):
     _need_cuda(rows, d_out, offsets)
     B = offsets.numel() - 1
     dT = torch.empty((B, 4), dtype=torch.float32, device=rows.device)
-    _lib.call("spg_rows_xy_transform_bwd", rows, _c(d_out), rows.shape[1], offsets, dT, B, _lib.current_stream())
+    d_out = _c(d_out)
+    _lib.call("spg_rows_xy_transform_bwd", rows, rows.shape[1], d_out, d_out.shape[1], offsets, dT, B,
+              _lib.current_stream())
     return dT
 
 
