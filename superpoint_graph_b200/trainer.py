@@ -135,8 +135,20 @@ class Trainer(object):
         self._graphs = {}
         self.class_weights = class_weights
         self.pg, self.world_size = process_group, world_size
+        self._fused_ar = None
         if world_size > 1:  # one-time setup collective: guarantee identical replicas
             torch.distributed.broadcast(self.flat, 0, group=process_group)
+            if self.flat.is_cuda and ops.USE_FUSED_ALLREDUCE[0]:
+                # gradient buffer in symmetric memory: all-reduce + clamp + Adam become ONE kernel over
+                # NVLink peer pointers; any failure to set that up leaves the NCCL path in place
+                try:
+                    self._fused_ar = ops.FusedAllreduce(self.flat.numel(), self.flat.device,
+                                                        process_group or torch.distributed.group.WORLD)
+                    self.flat_grad = self._fused_ar.grad
+                except Exception as ex:  # pragma: no cover (depends on the box's P2P capabilities)
+                    import warnings
+                    warnings.warn("fused all-reduce unavailable (%r): using torch.distributed.all_reduce" % (ex,))
+                    self._fused_ar = None
         self.embedder = CloudEmbedder(SimpleNamespace(cuda=1, ptn_mem_monger=args.ptn_mem_monger))
 
     def forward(self, db):
@@ -184,8 +196,12 @@ class Trainer(object):
     def apply_update(self):
         """One all-reduce of the flat gradient (scene-parallel ranks), then clamp + Adam in one
         kernel (gradient averaged by 1/world before the clamp, as main.py:210-213 on one GPU)."""
-        self.reduce_gradients()
         self.step_count += 1
+        if self._fused_ar is not None:
+            self._fused_ar.step_(self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev, lr=self.args.lr,
+                                 weight_decay=self.args.wd, grad_clip=self.args.grad_clip)
+            return
+        self.reduce_gradients()
         ops.clamp_adam_dev_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
                             lr=self.args.lr, weight_decay=self.args.wd, grad_clip=self.args.grad_clip,
                             grad_scale=1.0 / self.world_size)
@@ -254,7 +270,7 @@ class Trainer(object):
     def replay(self, key):
         g, db, loss, logits = self._graphs[key]
         g.replay()
-        self.apply_update()
+        self.apply_update()  # (NCCL path: outside the graph; fused path: one more kernel launch)
         return loss, logits
 
     @torch.no_grad()
