@@ -10,7 +10,7 @@ from superpoint_graph_b200.synthetic import make_batch  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 dev = torch.device("cuda:0")
-b = make_batch(n_nodes=n, seed=5)
+b = make_batch(n_nodes=n, seed=5, npts=1, minpts=1)
 N, E, H = b["degs"].numel(), b["idxn"].numel(), 32
 graph = ops.EccGraph(b["idxn"], None, b["degs"], n_in=N)
 x, g = torch.randn(N, H, device=dev), torch.randn(N, H, device=dev)
