@@ -11,10 +11,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// fp32 -> tf32 (10-bit mantissa), round to nearest with ties away from zero — what cvt.rna.tf32.f32
+// computes, written as two full-rate integer instructions: the conversion unit issues only a fraction
+// of a warp per clock, and a 3xTF32 producer needs two conversions per element (measured: the
+// conversions alone cost 2/3 of the MMA time of a K chunk).  Adding half a tf32 ulp to the magnitude bits
+// and clearing the 13 low bits rounds the sign-magnitude value half away from zero; a carry out of the
+// mantissa bumps the exponent, as rounding up to the next binade must.
 __device__ __forceinline__ uint32_t to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
+    return (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -415,7 +415,7 @@ def test_pointnet_ragged_csr(golden_dir, dev):
     out.backward(gy.to(dev))
     # (float32 oracle, BatchNorm over 1.5e4 points, max-pool ties: see tests/test_gpu_shapes.py's docstring)
     close_grads({k: p.grad for k, p in net.named_parameters()},
-                {k: v.grad for k, v in sd.items() if v.requires_grad}, 1e-2)
+                {k: v.grad for k, v in sd.items() if v.requires_grad}, 3e-2)
 
 
 def test_pointnet_s3dis_widths_vs_oracle(dev):
