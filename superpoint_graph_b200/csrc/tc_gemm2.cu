@@ -30,6 +30,15 @@
 // or s1/s2.  Round 1 wrote a partial per (tile, warp) — 3768 per column — and needed a two-level
 // merge plus separate BatchNorm-backward reduce/apply passes (0.85 of 1.95 ms per step).
 //
+// Measured limits (profiles/README.md, round 2): in steady state (1.29 M rows) the forward variant holds the
+// tensor pipe 35 % busy while the shared-memory data pipe is ~80 % busy (LSU 45 % + tensor-core operand
+// reads 34 %): 3xTF32 reads A and B twice per K chunk on top of the producers' 32 KB of stores per chunk.
+// Tried and rejected (each measured slower or equal): an A-operand ring in tensor memory written by
+// thread-per-row producers (uncoalesced 64-byte row segments: 585 -> 675 us at 1.29 M rows), L2 prefetch of
+// the rows 10 chunks ahead, a 3-deep register ring for the two-operand prologue (spills at the 128-register
+// cap of a 13-warp CTA), an in-kernel grid barrier for the merge (cooperative launch serialises against the
+// side stream).
+//
 // Reference semantics: nn.Conv1d(k=1)+BatchNorm1d+ReLU stacks of learning/pointnet.py:27-37,83-96
 // and their autograd backward.
 #include <cuda.h>
