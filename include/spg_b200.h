@@ -393,12 +393,23 @@ int spg_allreduce_clamp_adam(const float* const* peer_grads, uint32_t* const* pe
  * products are 3xTF32 on tcgen05 (fp32-equivalent).  weight_image = for each layer the
  * spg_tc_pack_weights_scaled image ([K_l/32][hi|lo][N_l][32 floats]; K_0 = 32, k_valid = F) back to
  * back (spg_pointnet_fused_image_rows(...) * 32 floats); bias = the folded biases back to back;
- * widths: HOST int32 array, every width in {64,128,256}, inner widths <= 128, at most 6 layers.     */
+ * widths: HOST int32 array, every width in {32,64,128,256}, inner widths <= 128, at most 6 layers.   */
 int spg_pointnet_fused_supported(int n_features, int n_points, int n_layers, const int32_t* widths);
 int64_t spg_pointnet_fused_image_rows(int n_features, int n_layers, const int32_t* widths);
 int spg_pointnet_fused_eval(const float* clouds, int64_t n_clouds, int n_features, int n_points, const float* T,
                             int add_eye, const float* weight_image, const float* bias, int n_layers,
                             const int32_t* widths, float* pooled, int64_t ldp, spg_stream_t stream);
+/* bf16 arithmetic for the same trunk (BASELINE configs[3]): bf16 operands, fp32 accumulation in TMEM
+ * (tcgen05.mma kind::f16, one MMA per product), activations between layers as bf16 on chip; inputs
+ * fp32 [B,F,128], pooled output fp32.  weight_image: per layer [K_l/64][N_l][64] bf16 from
+ * spg_tc_pack_weights_bf16 (K_0 = 64 with k_valid = F; a layer that follows a 32-wide one has K = 64 with
+ * k_valid = 32).  Agreement with the fp32 path is bounded by bf16 rounding (~1e-2), not 1e-4.          */
+int64_t spg_pointnet_fused_bf16_image_rows(int n_features, int n_layers, const int32_t* widths);
+int spg_tc_pack_weights_bf16(const float* W, int64_t ldw, const float* row_scale, int N, int K, int k_valid,
+                             void* image, spg_stream_t stream);
+int spg_pointnet_fused_eval_bf16(const float* clouds, int64_t n_clouds, int n_features, int n_points, const float* T,
+                                 int add_eye, const void* weight_image, const float* bias, int n_layers,
+                                 const int32_t* widths, float* pooled, int64_t ldp, spg_stream_t stream);
 /* Ragged superpoints (north_star: CSR offset array instead of the reference's resample-to-ptn_npts,
  * learning/spg.py:209-214): point rows [P, ld] of all superpoints back to back, offsets int64 [B+1].
  *   spg_segmax_csr_fwd: pooled[b,c] = max over the segment's rows of relu?(Y*scale+shift); argmax_row

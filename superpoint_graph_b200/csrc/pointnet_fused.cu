@@ -188,9 +188,9 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                             const uint32_t dst = w_u + s * PF_STAGE_BYTES;
                             // image rows of this layer: [(kc*2 + half)*N + n]
                             for (int half = 0; half < 2; ++half)
-                                for (int sub = 0; sub < ntile / 64; ++sub)
-                                    pf_tma_2d(dst + (uint32_t)(half * ntile + sub * 64) * (PF_KC * 4), &wmap, 0,
-                                              Ly.w_row + (kc * 2 + half) * Ly.N + nt * ntile + sub * 64, w_full(s));
+                                for (int sub = 0; sub < ntile / 32; ++sub)  // TMA boxes of 32 rows
+                                    pf_tma_2d(dst + (uint32_t)(half * ntile + sub * 32) * (PF_KC * 4), &wmap, 0,
+                                              Ly.w_row + (kc * 2 + half) * Ly.N + nt * ntile + sub * 32, w_full(s));
                         }
                 }
             }
@@ -350,6 +350,252 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
     }
 }
 
+// ------------------------------------------------------------------ bf16 variant (configs[3] arithmetic)
+// Same trunk with bf16 operands and fp32 accumulation: tcgen05.mma kind::f16, ONE MMA per product.
+// Activations travel between layers as bf16 in shared memory (K-major SWIZZLE_128B, 64 elements per
+// 128-byte row, written by the thread that owns the row); the weight image is bf16 (a quarter of the
+// 3xTF32 stream), 8-stage TMA ring.  Inputs and every layer output are rounded to bf16 (8-bit mantissa):
+// results agree with the fp32 path to ~1e-2 (tests state the bound), not to 1e-4.
+constexpr int PB_KC = 64;                                   // bf16 elements per K chunk (128-byte row)
+constexpr int PB_STAGES = 8;
+constexpr int PB_STAGE_BYTES = PF_NT * 128;                 // one (N-tile, K-chunk) weight block = 16 KB
+constexpr int PB_A_CHUNK_BYTES = PF_ROWS * 128;             // 16 KB
+constexpr int PB_A_BYTES = (PF_MAXK / PB_KC) * PB_A_CHUNK_BYTES;  // 32 KB
+
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    // c = F32 (1 << 4), a = b = BF16 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {  // e0 -> low half (lower address)
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+pointnet_fused_bf16_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
+                           const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    // [A operand 32 KB][weight ring 8 x 16 KB][input tiles 2 x 8 KB][bias][pool scratch]
+    uint8_t* a_s = smem;
+    uint8_t* w_s = a_s + PB_A_BYTES;
+    uint8_t* x_s = w_s + PB_STAGES * PB_STAGE_BYTES;
+    float* bias_s = reinterpret_cast<float*>(x_s + 2 * PF_X_BYTES);
+    float* pool_s = bias_s + PF_MAX_BIAS;
+    __shared__ __align__(8) uint64_t bars[2 * PB_STAGES + 4 + 1 + PF_MAX_TILES];
+    __shared__ uint32_t tmem_base_s;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t bars_u = smem_u32(&bars[0]);
+    auto w_full = [&](int s) { return bars_u + 8u * (uint32_t)s; };
+    auto w_empty = [&](int s) { return bars_u + 8u * (uint32_t)(PB_STAGES + s); };
+    auto x_full = [&](int s) { return bars_u + 8u * (uint32_t)(2 * PB_STAGES + s); };
+    auto x_empty = [&](int s) { return bars_u + 8u * (uint32_t)(2 * PB_STAGES + 2 + s); };
+    const uint32_t a_ready = bars_u + 8u * (2 * PB_STAGES + 4);
+    auto acc_full = [&](int nt) { return bars_u + 8u * (uint32_t)(2 * PB_STAGES + 5 + nt); };
+    if (t == 0) {
+        for (int s = 0; s < PB_STAGES; ++s) {
+            mbar_init(w_full(s), 1);
+            mbar_init(w_empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(x_full(s), 1);
+            mbar_init(x_empty(s), PF_ACT_WARPS);
+        }
+        for (int s = 0; s < PF_MAX_TILES; ++s) mbar_init(acc_full(s), 1);
+        mbar_init(a_ready, PF_ACT_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = t; i < p.n_bias; i += PF_THREADS) bias_s[i] = p.bias[i];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t a_u = smem_u32(a_s), w_u = smem_u32(w_s), x_u = smem_u32(x_s);
+
+    if (warp == PF_ACT_WARPS) {
+        if (lane == 0) {  // ---- TMA producer
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+            uint32_t it = 0, ci = 0;
+            for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++ci) {
+                const int xb = ci & 1;
+                mbar_wait(x_empty(xb), ((ci >> 1) & 1) ^ 1);
+                pf_expect_tx(x_full(xb), (uint32_t)(p.F * PF_ROWS * 4));
+                pf_tma_2d(x_u + xb * PF_X_BYTES, &xmap, 0, (int)(b * p.F), x_full(xb));
+                for (int l = 0; l < p.n_layers; ++l) {
+                    const PfLayer& Ly = p.L[l];
+                    const int ntile = Ly.N < PF_NT ? Ly.N : PF_NT;
+                    for (int nt = 0; nt < Ly.N / ntile; ++nt)
+                        for (int kc = 0; kc < Ly.K / PB_KC; ++kc, ++it) {
+                            const int s = it % PB_STAGES;
+                            mbar_wait(w_empty(s), ((it / PB_STAGES) & 1) ^ 1);
+                            pf_expect_tx(w_full(s), (uint32_t)(ntile * 128));
+                            // image rows of this layer: [kc*N + n], 128 bytes each; boxes of 32 rows
+                            for (int sub = 0; sub < ntile / 32; ++sub)
+                                pf_tma_2d(w_u + (uint32_t)(s * PB_STAGE_BYTES + sub * 32 * 128), &wmap, 0,
+                                          Ly.w_row + kc * Ly.N + nt * ntile + sub * 32, w_full(s));
+                        }
+                }
+            }
+        }
+    } else if (warp == PF_ACT_WARPS + 1) {
+        if (lane == 0) {  // ---- MMA issuer
+            uint32_t it = 0, q = 0;
+            for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+                for (int l = 0; l < p.n_layers; ++l, ++q) {
+                    const PfLayer& Ly = p.L[l];
+                    const int ntile = Ly.N < PF_NT ? Ly.N : PF_NT;
+                    const uint32_t idesc = umma_idesc_bf16(PF_ROWS, ntile);
+                    mbar_wait(a_ready, q & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int nt = 0; nt < Ly.N / ntile; ++nt) {
+                        const uint32_t d = tmem_base + (uint32_t)(nt * PF_NT);
+                        for (int kc = 0; kc < Ly.K / PB_KC; ++kc, ++it) {
+                            const int s = it % PB_STAGES;
+                            mbar_wait(w_full(s), (it / PB_STAGES) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t a0 = a_u + (uint32_t)kc * PB_A_CHUNK_BYTES;
+                            const uint32_t b0 = w_u + (uint32_t)s * PB_STAGE_BYTES;
+#pragma unroll
+                            for (int ks = 0; ks < PB_KC / 16; ++ks)  // K = 16 bf16 = 32 bytes per instruction
+                                umma_bf16(d, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc,
+                                          (kc | ks) ? 1u : 0u);
+                            umma_commit(w_empty(s));
+                        }
+                        umma_commit(acc_full(nt));
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- activation warps: one thread per (point, half of the 32-column blocks)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // 32 consecutive channels starting at channel col0 of the next A operand: 4 x 16 bytes of packed bf16
+        auto store_block = [&](int col0, const float (&o)[32]) {
+            const uint32_t base = a_u + (uint32_t)(col0 / PB_KC) * PB_A_CHUNK_BYTES;
+            const int c16_0 = (col0 % PB_KC) / 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t q0 = pack_bf16x2(o[8 * j], o[8 * j + 1]), q1 = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+                const uint32_t q2 = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), q3 = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + sw128_off(row, c16_0 + j)),
+                             "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+            }
+        };
+        auto publish_a = [&]() {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) pf_arrive(a_ready);
+        };
+        const float zeros[32] = {0.f};
+        uint32_t ci = 0, acc_cnt[PF_MAX_TILES] = {0u, 0u};
+        for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++ci) {
+            const int xb = ci & 1;
+            mbar_wait(x_full(xb), (ci >> 1) & 1);
+            const float* xin = reinterpret_cast<const float*>(x_s + xb * PF_X_BYTES);
+            float v[32];
+#pragma unroll
+            for (int f = 0; f < 32; ++f) v[f] = (f < PF_MAXF && f < p.F) ? xin[f * PF_ROWS + row] : 0.f;
+            __syncwarp();
+            if (lane == 0) pf_arrive(x_empty(xb));
+            if (p.T && p.F >= 2) {
+                const float eye = p.add_eye ? 1.f : 0.f;
+                const float t00 = p.T[b * 4 + 0] + eye, t01 = p.T[b * 4 + 1], t10 = p.T[b * 4 + 2],
+                            t11 = p.T[b * 4 + 3] + eye;
+                const float x0 = v[0], x1 = v[1];
+                v[0] = fmaf(x0, t00, x1 * t10);
+                v[1] = fmaf(x0, t01, x1 * t11);
+            }
+            if (half == 0) store_block(0, v); else store_block(32, zeros);  // chunk 0: features | zero padding
+            publish_a();
+            for (int l = 0; l < p.n_layers; ++l) {
+                const PfLayer& Ly = p.L[l];
+                const int ntile = Ly.N < PF_NT ? Ly.N : PF_NT;
+                const bool last = l + 1 == p.n_layers;
+                for (int nt = 0; nt < Ly.N / ntile; ++nt) {
+                    mbar_wait(acc_full(nt), acc_cnt[nt] & 1);
+                    ++acc_cnt[nt];
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int cb = half; cb < ntile / 32; cb += PF_ACT_WARPS / 4) {
+                        uint32_t r[32];
+                        tmem_ld32(lane_base + (uint32_t)(nt * PF_NT + cb * 32), r);
+                        const int col0 = nt * ntile + cb * 32;
+                        const float* bs = bias_s + Ly.b_off + col0;
+                        if (!last) {
+                            float o[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[j] = fmaxf(__uint_as_float(r[j]) + bs[j], 0.f);
+                            store_block(col0, o);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float o = fmaxf(__uint_as_float(r[j]) + bs[j], 0.f);
+                                const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(o));
+                                if (lane == j) pool_s[quarter * 256 + col0 + j] = __uint_as_float(m);
+                            }
+                        }
+                    }
+                    // a 32-wide layer fills only half of the next 64-element K chunk: zero the other half
+                    if (!last && Ly.N == 32 && half == 1) store_block(32, zeros);
+                }
+                if (!last) {
+                    publish_a();
+                } else {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(PF_ACT_WARPS * 32) : "memory");
+                    for (int c = t; c < Ly.N; c += PF_ACT_WARPS * 32) {
+                        const float m = fmaxf(fmaxf(pool_s[c], pool_s[256 + c]), fmaxf(pool_s[512 + c], pool_s[768 + c]));
+                        p.pooled[b * p.ldp + c] = m;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(PF_ACT_WARPS * 32) : "memory");
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// bf16 weight image of diag(row_scale) * W: for every 64-element K chunk [N rows][128 B], SWIZZLE_128B
+__global__ void pack_weights_bf16_kernel(const float* __restrict__ W, int64_t ldw,
+                                         const float* __restrict__ row_scale, int N, int K, int k_valid,
+                                         uint16_t* __restrict__ img) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int n = (int)(i / K), k = (int)(i % K);
+    float v = 0.f;
+    if (k < k_valid) v = W[(int64_t)n * ldw + k] * (row_scale ? row_scale[n] : 1.f);
+    const uint32_t pk = pack_bf16x2(v, 0.f);
+    const int kc = k / PB_KC, kk = k % PB_KC;
+    img[(int64_t)kc * N * PB_KC + (sw128_off(n, kk >> 3) >> 1) + (kk & 7)] = (uint16_t)(pk & 0xffffu);
+}
+
 typedef CUresult (*PfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -367,15 +613,16 @@ static PfEncodeFn pf_encode() {
     return fn;
 }
 
-static int pf_map_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
-                     uint32_t box_rows) {
+static int pf_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                     uint32_t box_rows, bool bf16 = false) {
     PfEncodeFn fn = pf_encode();
     if (!fn) return SPG_E_UNSUPPORTED;
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 4};
+    const cuuint64_t strides[1] = {cols * (bf16 ? 2 : 4)};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+    const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SPG_OK : SPG_E_BADARG;
@@ -393,7 +640,7 @@ int spg_pointnet_fused_supported(int n_features, int n_points, int n_layers, con
     int total = 0;
     for (int l = 0; l < n_layers; ++l) {
         const int n = widths[l];
-        if (n != 64 && n != 128 && n != 256) return 0;
+        if (n != 32 && n != 64 && n != 128 && n != 256) return 0;
         if (l + 1 < n_layers && n > PF_MAXK) return 0;  // a layer's output is the next layer's K
         total += n;
     }
@@ -435,30 +682,75 @@ int spg_pointnet_fused_eval(const float* clouds, int64_t n_clouds, int n_feature
     a.F = n_features; a.B = n_clouds; a.T = T; a.add_eye = add_eye; a.bias = bias; a.n_bias = boff;
     a.pooled = pooled; a.ldp = ldp;
     CUtensorMap wmap, xmap;
-    int rc = pf_map_2d(&wmap, weight_image, PF_KC, (uint64_t)row, PF_KC, 64);
+    int rc = pf_map_2d(&wmap, weight_image, PF_KC, (uint64_t)row, PF_KC, 32);
     if (rc) return rc;
     rc = pf_map_2d(&xmap, clouds, PF_ROWS, (uint64_t)(n_clouds * n_features), PF_ROWS, (uint32_t)n_features);
     if (rc) return rc;
-    static int a_in_tmem = -1;
-    if (a_in_tmem < 0) {
-        const char* env = getenv("SPG_FUSED_A_TMEM");
-        a_in_tmem = env ? atoi(env) : 1;
-    }
     const int64_t grid = n_clouds < kNumSMs ? n_clouds : kNumSMs;
-    const int tail = 2 * PF_X_BYTES + (PF_MAX_BIAS + 4 * 256) * 4;
-    if (a_in_tmem) {
-        const int smem = PF_STAGES_TMEM_A * PF_STAGE_BYTES + tail;
-        cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel<true>, (unsigned)grid, PF_THREADS,
-                   smem, a, wmap, xmap);
-    } else {
-        const int smem = PF_A_BYTES + PF_STAGES_SMEM_A * PF_STAGE_BYTES + tail;
-        cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel<false>, (unsigned)grid, PF_THREADS,
-                   smem, a, wmap, xmap);
+    const int smem = PF_STAGES_TMEM_A * PF_STAGE_BYTES + 2 * PF_X_BYTES + (PF_MAX_BIAS + 4 * 256) * 4;
+    cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel<true>, (unsigned)grid, PF_THREADS, smem,
+               a, wmap, xmap);
+    return launch_status();
+}
+
+/* bf16 twins (spg_b200.h): K chunks of 64 elements; a 32-wide layer is followed by a zero-padded chunk */
+int64_t spg_pointnet_fused_bf16_image_rows(int n_features, int n_layers, const int32_t* widths) {
+    (void)n_features;
+    int64_t rows = 0;
+    int k = PB_KC;
+    for (int l = 0; l < n_layers; ++l) {
+        rows += (int64_t)(k / PB_KC) * widths[l];
+        k = widths[l] < PB_KC ? PB_KC : widths[l];
     }
+    return rows;
+}
+
+int spg_tc_pack_weights_bf16(const float* W, int64_t ldw, const float* row_scale, int N, int K, int k_valid,
+                             void* image, spg_stream_t stream) {
+    if (!W || !image || N <= 0 || K <= 0 || k_valid <= 0 || k_valid > K) return SPG_E_BADARG;
+    if (K % PB_KC != 0 || N % 8 != 0) return SPG_E_UNSUPPORTED;
+    const int64_t total = (int64_t)N * K;
+    SPG_LAUNCH(K_TC_PACK, (cudaStream_t)stream, pack_weights_bf16_kernel, (unsigned)ceil_div64(total, 256), 256, 0, W,
+               ldw, row_scale, N, K, k_valid, (uint16_t*)image);
+    return launch_status();
+}
+
+int spg_pointnet_fused_eval_bf16(const float* clouds, int64_t n_clouds, int n_features, int n_points, const float* T,
+                                 int add_eye, const void* weight_image, const float* bias, int n_layers,
+                                 const int32_t* widths, float* pooled, int64_t ldp, spg_stream_t stream) {
+    if (n_clouds < 0 || !widths) return SPG_E_BADARG;
+    if (!spg_pointnet_fused_supported(n_features, n_points, n_layers, widths)) return SPG_E_UNSUPPORTED;
+    if (n_clouds == 0) return SPG_OK;
+    if (!clouds || !weight_image || !bias || !pooled || ldp < widths[n_layers - 1]) return SPG_E_BADARG;
+    if (((uintptr_t)clouds | (uintptr_t)weight_image) & 15) return SPG_E_ALIGN;
+    if (n_clouds * n_features >= (1ll << 31)) return SPG_E_UNSUPPORTED;
+    PfArgs a;
+    a.n_layers = n_layers;
+    int k = PB_KC, row = 0, boff = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        a.L[l].K = k;
+        a.L[l].N = widths[l];
+        a.L[l].w_row = row;
+        a.L[l].b_off = boff;
+        row += (k / PB_KC) * widths[l];
+        boff += widths[l];
+        k = widths[l] < PB_KC ? PB_KC : widths[l];
+    }
+    a.F = n_features; a.B = n_clouds; a.T = T; a.add_eye = add_eye; a.bias = bias; a.n_bias = boff;
+    a.pooled = pooled; a.ldp = ldp;
+    CUtensorMap wmap, xmap;
+    int rc = pf_map_2d(&wmap, weight_image, PB_KC, (uint64_t)row, PB_KC, 32, true);
+    if (rc) return rc;
+    rc = pf_map_2d(&xmap, clouds, PF_ROWS, (uint64_t)(n_clouds * n_features), PF_ROWS, (uint32_t)n_features);
+    if (rc) return rc;
+    const int64_t grid = n_clouds < kNumSMs ? n_clouds : kNumSMs;
+    const int smem = PB_A_BYTES + PB_STAGES * PB_STAGE_BYTES + 2 * PF_X_BYTES + (PF_MAX_BIAS + 4 * 256) * 4;
+    cudaError_t e = cudaFuncSetAttribute(pointnet_fused_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_bf16_kernel, (unsigned)grid, PF_THREADS, smem, a,
+               wmap, xmap);
     return launch_status();
 }
 

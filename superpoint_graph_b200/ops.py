@@ -802,33 +802,49 @@ def pointnet_fused_supported(F, L, widths):
 
 
 _FUSED_IMAGES = {}  # parameter versions -> (weight image, folded bias, widths tensor)
+EVAL_BF16 = [False]  # eval-mode PointNet trunk in bf16 arithmetic (Trainer(dtype="bf16") sets it around eval_step)
 
 
-def pointnet_fused_image(layers, F):
+def pointnet_fused_image(layers, F, bf16=False):
     """layers: [(W [N,K] (2-D view), bias|None, bn_module|None)] of a Conv1d(k=1)+BatchNorm+ReLU chain in eval
     mode.  Returns (image, bias, widths): BatchNorm folded into weights and bias (scale = gamma/sqrt(rv+eps),
-    bias' = bias*scale + beta - rm*scale), packed for spg_pointnet_fused_eval.  Cached on the tensors'
-    version counters (eval weights do not change between batches)."""
+    bias' = bias*scale + beta - rm*scale), packed for spg_pointnet_fused_eval (fp32: tf32 hi|lo blocks of 32
+    floats) or spg_pointnet_fused_eval_bf16 (bf16 blocks of 64 elements).  Cached on the tensors' version
+    counters (eval weights do not change between batches)."""
     key = []
     for W, b, bn in layers:
         ts = [W, b] + ([bn.running_mean, bn.running_var, bn.weight, bn.bias] if bn is not None else [])
         key += [(x.data_ptr(), x._version) for x in ts if x is not None]
-    key = (int(F),) + tuple(key)
+    key = (int(F), bool(bf16)) + tuple(key)
     ent = _FUSED_IMAGES.get(key)
     if ent is not None:
         return ent
     dev = layers[0][0].device
+    L = _lib.lib()
     widths = torch.tensor([int(W.shape[0]) for W, _, _ in layers], dtype=torch.int32)
-    rows = int(_lib.lib().spg_pointnet_fused_image_rows(int(F), len(layers), widths.data_ptr()))
-    image = torch.empty(rows * 32, dtype=torch.float32, device=dev)
+    if bf16:
+        rows = int(L.spg_pointnet_fused_bf16_image_rows(int(F), len(layers), widths.data_ptr()))
+        image = torch.empty(rows * 64, dtype=torch.bfloat16, device=dev)
+        kc = 64
+    else:
+        rows = int(L.spg_pointnet_fused_image_rows(int(F), len(layers), widths.data_ptr()))
+        image = torch.empty(rows * 32, dtype=torch.float32, device=dev)
+        kc = 32
     bias = torch.empty(int(widths.sum()), dtype=torch.float32, device=dev)
-    row, boff, K = 0, 0, 32
+    row, boff, K = 0, 0, kc
     for W, b, bn in layers:
         N, kv = int(W.shape[0]), int(W.shape[1])
         scale = shift = None
         if bn is not None:
             scale, shift = bn_fold(bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps)
-        _lib.call("spg_tc_pack_weights_scaled", W, W.stride(0), scale, N, K, kv, image[row * 32:], _lib.current_stream())
+        if bf16:
+            _lib.call("spg_tc_pack_weights_bf16", W, W.stride(0), scale, N, K, kv, image[row * 64:],
+                      _lib.current_stream())
+            row += (K // 64) * N
+        else:
+            _lib.call("spg_tc_pack_weights_scaled", W, W.stride(0), scale, N, K, kv, image[row * 32:],
+                      _lib.current_stream())
+            row += (K // 32) * 2 * N
         bsl = bias[boff:boff + N]
         if b is not None:
             affine_act(b.detach().reshape(1, N), N, 1, N, scale, shift, False, out=bsl, ldo=N)
@@ -836,9 +852,8 @@ def pointnet_fused_image(layers, F):
             bsl.copy_(shift)
         else:
             zero_(bsl)
-        row += (K // 32) * 2 * N
         boff += N
-        K = N
+        K = max(N, kc) if bf16 else N
     if len(_FUSED_IMAGES) > 64:
         _FUSED_IMAGES.clear()
     _FUSED_IMAGES[key] = (image, bias, widths)
@@ -846,9 +861,11 @@ def pointnet_fused_image(layers, F):
 
 
 def pointnet_fused_eval(clouds, T, image, bias, widths, pooled, ldp):
-    """pooled[b, :widths[-1]] = max over points of the folded conv chain on clouds[b] (xy transformed by T+I)."""
+    """pooled[b, :widths[-1]] = max over points of the folded conv chain on clouds[b] (xy transformed by T+I);
+    the image's dtype selects the arithmetic (float32 image: 3xTF32, bfloat16 image: bf16)."""
     _need_cuda(clouds, image, bias, pooled, T)
     B, F, L = clouds.shape
-    _lib.call("spg_pointnet_fused_eval", clouds, B, F, L, None if T is None else _c(T), 1, image, bias,
+    name = "spg_pointnet_fused_eval_bf16" if image.dtype == torch.bfloat16 else "spg_pointnet_fused_eval"
+    _lib.call(name, clouds, B, F, L, None if T is None else _c(T), 1, image, bias,
               int(widths.numel()), widths.data_ptr(), pooled, ldp, _lib.current_stream())
     return pooled

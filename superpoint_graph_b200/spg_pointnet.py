@@ -350,12 +350,12 @@ def _fused_eval_forward(clouds, glob, nfeat_stn, groups, params):
     T = None
     if nfeat_stn > 0:
         cs, fs = stn_g
-        img, bias, widths = ops.pointnet_fused_image(_conv_layers(cs, params), F)
+        img, bias, widths = ops.pointnet_fused_image(_conv_layers(cs, params), F, bf16=ops.EVAL_BF16[0])
         Cs = cs[-1].cout
         pooled_s = torch.empty((B, Cs), dtype=torch.float32, device=dev)
         ops.pointnet_fused_eval(clouds, None, img, bias, widths, pooled_s, Cs)
         T = chain_forward(Deferred(pooled_s, Cs, Cs), B, fs, params, False, None).materialise(B)
-    img, bias, widths = ops.pointnet_fused_image(_conv_layers(conv_g, params), F)
+    img, bias, widths = ops.pointnet_fused_image(_conv_layers(conv_g, params), F, bf16=ops.EVAL_BF16[0])
     Ct = conv_g[-1].cout
     G = 0 if glob is None else glob.shape[1]
     ldp = _round4(Ct + G)

@@ -164,6 +164,9 @@ class Trainer(object):
     def compute_gradients(self, db):
         """Forward, loss, backward; gathers every parameter gradient into the flat buffer.
         Returns (loss[1], logits).  Purely local to this rank (no collective)."""
+        if self.dtype != "f32":
+            raise NotImplementedError("training runs in fp32 (3xTF32 on the tensor cores); bf16 arithmetic is "
+                                      "implemented for the inference forward only (Trainer.eval_step)")
         self.model.train()
         for p in self.params:
             p.grad = None
@@ -275,8 +278,15 @@ class Trainer(object):
 
     @torch.no_grad()
     def eval_step(self, db):
+        """Inference forward (main.py:229-264).  dtype "bf16": the PointNet trunk (the tensor-core part of
+        the step) runs in bf16 arithmetic with fp32 accumulation; everything behind the pooled rows stays
+        fp32."""
         self.model.eval()
-        return self.forward(db)
+        ops.EVAL_BF16[0] = self.dtype == "bf16"
+        try:
+            return self.forward(db)
+        finally:
+            ops.EVAL_BF16[0] = False
 
     # ---- optimizer state in torch.optim.Adam's layout (checkpoints of main.py:342-346,390-412)
     def optimizer_state_dict(self):

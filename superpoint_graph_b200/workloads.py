@@ -24,12 +24,18 @@ WORKLOADS = {
         title="configs[2]: Semantic3D-shaped inference, gru_10,f_8, F=11, eval mode, %(nodes)d superpoints",
         args=dict(model_config="gru_10,f_8", node_feats=11, ptn_nfeat_stn=11, classes=8),
         batch=dict(nfeat=11, n_classes=8, minpts=40), nodes=20000, train=False, dtype="f32"),
-    # configs[3]: vKITTI3D SPG training widths, batch 4 x hardcutoff 256, minpts 15, xyzXYZrgb (F=9)
+    # configs[3]: vKITTI3D SPG widths (vKITTI3D.md:46-50), batch 4 x hardcutoff 256, minpts 15, xyzXYZrgb (F=9).
+    # Training runs in fp32; the inference forward exists in bf16 arithmetic (PointNet trunk: kind::f16).
     "vkitti_train": dict(
-        title="configs[3]: vKITTI3D-shaped training step, gru_10_1_1_1_0,f_13, F=9, 4 scenes x %(quarter)d superpoints per GPU",
+        title="configs[3] widths: vKITTI3D-shaped training step, gru_10_1_1_1_0,f_13, F=9, fp32, 4 scenes x %(quarter)d superpoints per GPU",
         args=dict(node_feats=9, ptn_nfeat_stn=9, ptn_widths=[[64, 64, 128], [64, 32, 32]],
                   ptn_widths_stn=[[32, 64], [32, 16]]),
-        batch=dict(nfeat=9, n_classes=13, minpts=15), nodes=1024, train=True, dtype="bf16"),
+        batch=dict(nfeat=9, n_classes=13, minpts=15), nodes=1024, train=True, dtype="f32"),
+    "vkitti_eval": dict(
+        title="configs[3]: vKITTI3D-shaped inference (PointNet embeddings + ECC), gru_10_1_1_1_0,f_13, F=9, bf16 trunk, %(nodes)d superpoints per GPU",
+        args=dict(node_feats=9, ptn_nfeat_stn=9, ptn_widths=[[64, 64, 128], [64, 32, 32]],
+                  ptn_widths_stn=[[32, 64], [32, 16]]),
+        batch=dict(nfeat=9, n_classes=13, minpts=15), nodes=8192, train=False, dtype="bf16"),
     # configs[4]: synthetic sweep, S3DIS architecture, vector and matrix filters
     "sweep_vv": dict(
         title="configs[4]: synthetic sweep training step, gru_10_1_1_1_0,f_13, fp32, %(nodes)d superpoints per GPU",

@@ -646,6 +646,22 @@ def test_local_cloud_embedder_tiny_clouds(dev):
     emb = LocalCloudEmbedder(SimpleNamespace(ptn_nfeat_stn=2, stn_as_global=1))
     out = emb.run_batch(model, clouds.to(dev), glob.to(dev))
     close(out, ref, 2e-4)
+    # backward through the whole embedder (STN -> xy transform -> global features -> PointNet -> L2
+    # normalisation) against autograd of the oracle on the same state (supervized_partition.py:411-434 trains it)
+    sd_s = {k: v.clone().requires_grad_(nets_ref.is_param(k)) for k, v in sd_stn.items()}
+    sd_p = {k: v.clone().requires_grad_(nets_ref.is_param(k)) for k, v in sd_ptn.items()}
+    T = nets_ref.stn_forward(clouds[:, :2], sd_s, "", 2, 2, True)
+    xy = torch.bmm(clouds[:, :2].transpose(1, 2), T).transpose(1, 2)
+    ref2 = torch.nn.functional.normalize(nets_ref.pointnet_forward(
+        torch.cat([xy, clouds[:, 2:]], 1), torch.cat([glob, T.view(-1, 4)], 1), sd_p, pcfg, True))
+    gy = torch.randn(B, 4)
+    ref2.backward(gy)
+    model.zero_grad()
+    out.backward(gy.to(dev))
+    close_grads({"stn." + k: p.grad for k, p in model.stn.named_parameters()},
+                {"stn." + k: v.grad for k, v in sd_s.items() if v.requires_grad}, 2e-3)
+    close_grads({"ptn." + k: p.grad for k, p in model.ptn.named_parameters()},
+                {"ptn." + k: v.grad for k, v in sd_p.items() if v.requires_grad}, 2e-3)
 
 
 def test_cloud_embedder_mem_monger_same_gradients(dev):
