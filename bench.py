@@ -220,7 +220,18 @@ class CpuArm(object):
     def step(self, batch):
         """-> (loss | None, logits)"""
         if self.w["train"]:
-            return self.impl.train_step(batch) if self.kind == "reference" else self.impl.step(batch)
+            if self.kind == "reference":
+                try:
+                    return self.impl.train_step(batch)
+                except RuntimeError as ex:
+                    # the reference's matrix-filter backward does not run on torch >= 2 (index_add_ shape
+                    # check at learning/ecc/GraphConvModule.py:146, SURVEY.md 8(c)): time the oracle port
+                    if "source tensor shape must match" not in str(ex):
+                        raise
+                    self.kind, self.note = "port", ("the reference's matrix-filter backward fails on torch>=2 "
+                                                    "(ecc/GraphConvModule.py:146): oracle port timed instead")
+                    self._make()
+            return self.impl.step(batch)
         if self.kind == "reference":
             return None, self.impl.eval_step(batch)
         from oracle import nets_ref
@@ -229,6 +240,8 @@ class CpuArm(object):
                                               False, ecc_mode="loop")
 
     def describe(self):
+        if getattr(self, "note", None):
+            return "oracle port of the reference CPU path (oracle/nets_ref, ecc_mode=loop); " + self.note
         if self.kind == "reference":
             return ("the reference's own modules (baseline/_ref: learning/pointnet.py, graphnet.py, modules.py, "
                     "ecc/*; use_pyg=0, cuda=False) through CloudEmbedder.run / GraphNetwork / cross_entropy / "

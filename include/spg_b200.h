@@ -410,6 +410,11 @@ int spg_tc_pack_weights_bf16(const float* W, int64_t ldw, const float* row_scale
 int spg_pointnet_fused_eval_bf16(const float* clouds, int64_t n_clouds, int n_features, int n_points, const float* T,
                                  int add_eye, const void* weight_image, const float* bias, int n_layers,
                                  const int32_t* widths, float* pooled, int64_t ldp, spg_stream_t stream);
+/* clouds_grad[b,f,l] = rows_grad[b*L+l, f]: the input gradient of a PointNet without an internal transformer
+ * back in the reference's [B,F,L] layout (autograd of learning/pointnet.py:126 w.r.t. its input; needed by
+ * LocalCloudEmbedder, whose external STN is trained through it, pointnet.py:189-207).                    */
+int spg_rows_to_clouds(const float* rows, int64_t ld, float* clouds, int64_t B, int F, int L,
+                       spg_stream_t stream);
 /* Ragged superpoints (north_star: CSR offset array instead of the reference's resample-to-ptn_npts,
  * learning/spg.py:209-214): point rows [P, ld] of all superpoints back to back, offsets int64 [B+1].
  *   spg_segmax_csr_fwd: pooled[b,c] = max over the segment's rows of relu?(Y*scale+shift); argmax_row

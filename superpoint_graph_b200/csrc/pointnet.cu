@@ -310,6 +310,25 @@ __global__ void rows_gather_kernel(const float* __restrict__ src, const int64_t*
     dst[i] = src[idx[r] * C + (i % C)];
 }
 
+// gradient w.r.t. the point-major rows back into the reference's [B, F, L] layout (inverse of cloud_rows
+// without a transformer): clouds_grad[b, f, l] = rows_grad[b*L + l, f].  grid (B, ceil(L/128)); block 128.
+__global__ void __launch_bounds__(kPtChunk)
+rows_to_clouds_kernel(const float* __restrict__ rows, int64_t ld, float* __restrict__ clouds, int F, int L) {
+    extern __shared__ float tile[];  // [F][129]
+    const int64_t b = blockIdx.x;
+    const int l0 = blockIdx.y * kPtChunk;
+    const int nl = min(kPtChunk, L - l0);
+    const float* src = rows + (b * L + l0) * ld;
+    for (int64_t i = threadIdx.x; i < (int64_t)nl * F; i += kPtChunk) {
+        const int l = (int)(i / F), f = (int)(i % F);
+        tile[f * (kPtChunk + 1) + l] = src[(int64_t)l * ld + f];
+    }
+    __syncthreads();
+    float* dst = clouds + b * (int64_t)F * L;
+    for (int f = 0; f < F; ++f)
+        for (int l = threadIdx.x; l < nl; l += kPtChunk) dst[(int64_t)f * L + l0 + l] = tile[f * (kPtChunk + 1) + l];
+}
+
 // ------------------------------------------------------------------ ragged (CSR) segments
 // north_star: "ragged segment boundaries carried as a CSR offset array and reduced by warp-shuffle
 // segmented max".  The reference never feeds ragged clouds (its loader resamples every superpoint to
@@ -544,6 +563,19 @@ int spg_rows_gather(const float* src, const int64_t* idx, float* dst, int64_t n_
     if (!src || !idx || !dst) return SPG_E_BADARG;
     SPG_LAUNCH(K_ROWS_GATHER, (cudaStream_t)stream, rows_gather_kernel,
                (unsigned)ceil_div64(n_dst * C, 256), 256, 0, src, idx, dst, n_dst, C);
+    return launch_status();
+}
+
+int spg_rows_to_clouds(const float* rows, int64_t ld, float* clouds, int64_t B, int F, int L,
+                       spg_stream_t stream) {
+    if (B < 0 || F <= 0 || L <= 0 || ld < F) return SPG_E_BADARG;
+    if (B == 0) return SPG_OK;
+    if (!rows || !clouds) return SPG_E_BADARG;
+    const size_t smem = sizeof(float) * (size_t)F * (kPtChunk + 1);
+    if (smem > 48 * 1024 || B > 2147483647ll) return SPG_E_UNSUPPORTED;
+    dim3 grid((unsigned)B, (unsigned)ceil_div64(L, kPtChunk));
+    SPG_LAUNCH(K_CLOUD_ROWS, (cudaStream_t)stream, rows_to_clouds_kernel, grid, kPtChunk, smem, rows, ld, clouds, F,
+               L);
     return launch_status();
 }
 

@@ -519,6 +519,13 @@ def cloud_rows(clouds, T, ld, add_eye=False):
     return rows
 
 
+def rows_to_clouds(rows, ld, B, F, L):
+    _need_cuda(rows)
+    out = torch.empty((B, F, L), dtype=torch.float32, device=rows.device)
+    _lib.call("spg_rows_to_clouds", rows, ld, out, B, F, L, _lib.current_stream())
+    return out
+
+
 def segmax_fwd(Y, ldy, B, L, C, scale, shift, relu, pooled, ldp):
     _need_cuda(Y, pooled)
     argmax = torch.empty((B, C), dtype=torch.int32, device=Y.device)

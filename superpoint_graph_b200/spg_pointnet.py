@@ -302,17 +302,26 @@ class _PointNetFunction(torch.autograd.Function):
         grads = [None] * len(params)
         gy = gy.contiguous()
         Ct, ld = saved["Ct"], saved["ld"]
+        want_clouds, want_glob = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if want_clouds and nfeat_stn > 0:
+            raise NotImplementedError("input gradient of a PointNet with an internal STN is not implemented "
+                                      "(the reference's callers never ask for it: the clouds are data)")
         g_pool = chain_backward(gy, gy.shape[1], B, fc_g, params, saved["fc"], True, grads)
-        g_rows = chain_backward(None, Ct, B * L, conv_g, params, saved["conv"], nfeat_stn > 0, grads,
+        # gradient w.r.t. the "global" inputs: the tail columns of the pooled row (pointnet.py:128-132)
+        g_glob = g_pool[:, Ct:Ct + saved["G"]].contiguous() if (want_glob and saved["G"] > 0) else None
+        g_rows = chain_backward(None, Ct, B * L, conv_g, params, saved["conv"], nfeat_stn > 0 or want_clouds, grads,
                                 pooled=(g_pool, g_pool.shape[1], saved["argmax"], B, L))
         del g_pool
+        g_clouds = None
         if nfeat_stn > 0:
             dT = ops.stn_apply_bwd(ctx.clouds, g_rows, g_rows.shape[1])
             del g_rows
             _stn_backward(dT, B, L, stn_g, params, saved, grads)
+        elif want_clouds:  # external transformer (LocalCloudEmbedder): hand the gradient back as [B, F, L]
+            g_clouds = ops.rows_to_clouds(g_rows, g_rows.shape[1], B, F, L)
         ctx.saved = None
         ctx.clouds = None
-        return (None, None, None, None, None) + tuple(grads)
+        return (g_clouds, g_glob, None, None, None) + tuple(grads)
 
 
 def _conv_layers(specs, params):
