@@ -38,11 +38,8 @@ constexpr int PF_NT = 128;            // accumulator tile width (TMEM columns pe
                                       // the activation warps drain tile t under the MMAs of tile t+1, but the next A
                                       // operand is written IN PLACE: every MMA of the layer must have finished first)
 constexpr int PF_MAX_TILES = 2;
-constexpr int PF_STAGES_SMEM_A = 2;   // weight ring depth (32 KB stages) next to a 128 KB shared-memory A operand
-constexpr int PF_STAGES_TMEM_A = 6;   // ... and when the A operand lives in tensor memory
+constexpr int PF_STAGES_TMEM_A = 6;   // weight ring depth (32 KB stages); the A operand lives in tensor memory
 constexpr int PF_STAGE_BYTES = 2 * PF_NT * PF_KC * 4;        // hi + lo of one (N-tile, K-chunk) = 32 KB
-constexpr int PF_A_CHUNK_BYTES = 2 * PF_ROWS * PF_KC * 4;    // hi + lo of one K chunk = 32 KB
-constexpr int PF_A_BYTES = (PF_MAXK / PF_KC) * PF_A_CHUNK_BYTES;  // 128 KB
 constexpr int PF_MAXF = 16;            // input features (S3DIS 14, Semantic3D 11, vKITTI 9)
 constexpr int PF_X_BYTES = PF_MAXF * PF_ROWS * 4;            // one input tile buffer (8 KB)
 constexpr int PF_MAX_LAYERS = 6;
@@ -82,20 +79,6 @@ __device__ __forceinline__ void pf_tma_2d(uint32_t dst, const CUtensorMap* map, 
         : "memory");
 }
 
-__device__ __forceinline__ void pf_split_store(uint32_t a_hi, int row, int c16, float4 v) {
-    uint4 hi, lo;
-    hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-    lo.x = to_tf32(v.x - __uint_as_float(hi.x));
-    lo.y = to_tf32(v.y - __uint_as_float(hi.y));
-    lo.z = to_tf32(v.z - __uint_as_float(hi.z));
-    lo.w = to_tf32(v.w - __uint_as_float(hi.w));
-    const uint32_t off = sw128_off(row, c16);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi.x), "r"(hi.y), "r"(hi.z),
-                 "r"(hi.w) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + PF_ROWS * PF_KC * 4 + off), "r"(lo.x),
-                 "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
-}
-
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -108,23 +91,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
-// ATM = true: the A operand (the layer's input activations, tf32 hi | lo) lives in TENSOR MEMORY: the
-// activation warps write the row they own with tcgen05.st (TMEM lane = point, column = channel — the
-// layout the accumulator row already has, no shared-memory transposition), the MMA reads it directly,
-// and all of shared memory goes to a 6-stage weight ring.  TMEM columns: [0,256) accumulators,
-// [256,384) A hi, [384,512) A lo.  ATM = false keeps A in shared memory (K-major SWIZZLE_128B).
-template <bool ATM>
+// The A operand (the layer's input activations, tf32 hi | lo) lives in TENSOR MEMORY: the activation warps
+// write the row they own with tcgen05.st (TMEM lane = point, column = channel — the layout the accumulator
+// row already has, no shared-memory transposition), the MMA reads it directly, and all of shared memory goes
+// to a 6-stage weight ring.  TMEM columns: [0,256) accumulators, [256,384) A hi, [384,512) A lo.
+// (A shared-memory A operand — K-major SWIZZLE_128B, 128 KB, 2-stage ring — was measured 7 % slower.)
 __global__ void __launch_bounds__(PF_THREADS, 1)
 pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                       const __grid_constant__ CUtensorMap xmap) {
-    constexpr int PF_STAGES = ATM ? PF_STAGES_TMEM_A : PF_STAGES_SMEM_A;
-    constexpr uint32_t TM_COLS = ATM ? 512u : 256u;
+    constexpr int PF_STAGES = PF_STAGES_TMEM_A;
+    constexpr uint32_t TM_COLS = 512u;
     constexpr uint32_t TM_AHI = 256u, TM_ALO = 384u;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
-    // [A operand 128 KB (shared-memory variant only)][weight ring][input tiles 2 x 8 KB][bias][pool scratch]
-    uint8_t* a_s = smem;
-    uint8_t* w_s = a_s + (ATM ? 0 : PF_A_BYTES);
+    // [weight ring 6 x 32 KB][input tiles 2 x 8 KB][bias][pool scratch]
+    uint8_t* w_s = smem;
     uint8_t* x_s = w_s + PF_STAGES * PF_STAGE_BYTES;
     float* bias_s = reinterpret_cast<float*>(x_s + 2 * PF_X_BYTES);
     float* pool_s = bias_s + PF_MAX_BIAS;  // [4 warps][256]
@@ -164,7 +145,7 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t a_u = smem_u32(a_s), w_u = smem_u32(w_s), x_u = smem_u32(x_s);
+    const uint32_t w_u = smem_u32(w_s), x_u = smem_u32(x_s);
 
     if (warp == PF_ACT_WARPS) {
         // ================================ TMA producer ================================
@@ -212,26 +193,17 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                             const int s = it % PF_STAGES;
                             mbar_wait(w_full(s), (it / PF_STAGES) & 1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t a_hi = a_u + (uint32_t)kc * PF_A_CHUNK_BYTES;
-                            const uint32_t a_lo = a_hi + PF_ROWS * PF_KC * 4;
                             const uint32_t b_hi = w_u + (uint32_t)s * PF_STAGE_BYTES;
                             const uint32_t b_lo = b_hi + (uint32_t)ntile * PF_KC * 4;
 #pragma unroll
                             for (int ks = 0; ks < PF_KC / 8; ++ks) {
                                 const uint32_t ko = ks * 32;
                                 const uint64_t dbh = umma_desc_k_sw128(b_hi + ko), dbl = umma_desc_k_sw128(b_lo + ko);
-                                if (ATM) {
-                                    const uint32_t th = tmem_base + TM_AHI + (uint32_t)(kc * PF_KC + ks * 8);
-                                    const uint32_t tl = tmem_base + TM_ALO + (uint32_t)(kc * PF_KC + ks * 8);
-                                    umma_tf32_ts(d, th, dbh, idesc, (kc | ks) ? 1u : 0u);
-                                    umma_tf32_ts(d, tl, dbh, idesc, 1u);
-                                    umma_tf32_ts(d, th, dbl, idesc, 1u);
-                                } else {
-                                    const uint64_t dah = umma_desc_k_sw128(a_hi + ko), dal = umma_desc_k_sw128(a_lo + ko);
-                                    umma_tf32(d, dah, dbh, idesc, (kc | ks) ? 1u : 0u);
-                                    umma_tf32(d, dal, dbh, idesc, 1u);
-                                    umma_tf32(d, dah, dbl, idesc, 1u);
-                                }
+                                const uint32_t th = tmem_base + TM_AHI + (uint32_t)(kc * PF_KC + ks * 8);
+                                const uint32_t tl = tmem_base + TM_ALO + (uint32_t)(kc * PF_KC + ks * 8);
+                                umma_tf32_ts(d, th, dbh, idesc, (kc | ks) ? 1u : 0u);
+                                umma_tf32_ts(d, tl, dbh, idesc, 1u);
+                                umma_tf32_ts(d, th, dbl, idesc, 1u);
                             }
                             umma_commit(w_empty(s));
                         }
@@ -266,28 +238,17 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
             const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
             auto store_chunk = [&](int kc, const float (&o)[32]) {
                 // 32 consecutive channels of this thread's row = K chunk kc of the next A operand
-                if (ATM) {
-                    uint32_t hi[32], lo[32];
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        hi[j] = to_tf32(o[j]);
-                        lo[j] = to_tf32(o[j] - __uint_as_float(hi[j]));
-                    }
-                    tmem_st32(lane_base + TM_AHI + (uint32_t)(kc * PF_KC), hi);
-                    tmem_st32(lane_base + TM_ALO + (uint32_t)(kc * PF_KC), lo);
-                } else {
-                    const uint32_t a_hi = a_u + (uint32_t)kc * PF_A_CHUNK_BYTES;
-#pragma unroll
-                    for (int c16 = 0; c16 < 8; ++c16)
-                        pf_split_store(a_hi, row, c16, make_float4(o[4 * c16], o[4 * c16 + 1], o[4 * c16 + 2], o[4 * c16 + 3]));
+                for (int j = 0; j < 32; ++j) {
+                    hi[j] = to_tf32(o[j]);
+                    lo[j] = to_tf32(o[j] - __uint_as_float(hi[j]));
                 }
+                tmem_st32(lane_base + TM_AHI + (uint32_t)(kc * PF_KC), hi);
+                tmem_st32(lane_base + TM_ALO + (uint32_t)(kc * PF_KC), lo);
             };
             auto publish_a = [&]() {
-                if (ATM) {
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                } else {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) pf_arrive(a_ready);
@@ -688,9 +649,9 @@ int spg_pointnet_fused_eval(const float* clouds, int64_t n_clouds, int n_feature
     if (rc) return rc;
     const int64_t grid = n_clouds < kNumSMs ? n_clouds : kNumSMs;
     const int smem = PF_STAGES_TMEM_A * PF_STAGE_BYTES + 2 * PF_X_BYTES + (PF_MAX_BIAS + 4 * 256) * 4;
-    cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(pointnet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel<true>, (unsigned)grid, PF_THREADS, smem,
+    SPG_LAUNCH(K_POINTNET_FUSED, (cudaStream_t)stream, pointnet_fused_kernel, (unsigned)grid, PF_THREADS, smem,
                a, wmap, xmap);
     return launch_status();
 }
