@@ -38,6 +38,10 @@ typedef void* spg_stream_t; /* cudaStream_t */
 /* ---------------------------------------------------------------- runtime */
 int spg_version(void);
 const char* spg_error_string(int code);
+/* Programmatic dependent launch of every kernel of the library (default on; environment SPG_PDL=0 switches it
+ * off): kernel n+1 of a stream is scheduled while kernel n runs and waits on the device (griddepcontrol.wait)
+ * for n's results.  No reference counterpart: the reference launches its kernels in plain stream order. */
+int spg_set_pdl(int enabled);
 /* cudaMemsetAsync(ptr, 0, bytes) on the stream. */
 int spg_zero(void* ptr, int64_t bytes, spg_stream_t stream);
 

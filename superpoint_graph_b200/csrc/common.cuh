@@ -96,8 +96,40 @@ bool vec_affine_act(const float* Y, int64_t ldy, const float* scale, const float
 
 }  // namespace spg
 
-#define SPG_LAUNCH(kid, stream_, kernel, grid, block, smem, ...)            \
-    do {                                                                     \
-        ::spg::LaunchScope _scope((kid), (stream_));                         \
-        kernel<<<(grid), (block), (smem), (stream_)>>>(__VA_ARGS__);         \
+// Programmatic dependent launch (sm_90+): every kernel of this library starts with pdl_entry() — wait until
+// the kernels it depends on have completed and flushed, then allow the NEXT kernel of the stream to be
+// scheduled — and is launched with programmaticStreamSerialization, so that the launch latency, block
+// scheduling and pre-wait set-up (barrier init, tensor-memory allocation) of kernel n+1 overlap kernel n.
+// The trigger comes AFTER the wait on purpose: at most one dependent grid is resident and waiting.
+// spg_set_pdl(0) switches the attribute off (plain stream order; the device instructions are then no-ops).
+#define SPG_PDL_ENTRY()                                          \
+    do {                                                         \
+        asm volatile("griddepcontrol.wait;" ::: "memory");       \
+        asm volatile("griddepcontrol.launch_dependents;" :::);   \
+    } while (0)
+
+namespace spg {
+bool pdl_enabled(int kernel_id);
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(int kid, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                          Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled(kid) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace spg
+
+#define SPG_LAUNCH(kid, stream_, kernel, grid, block, smem, ...)                                  \
+    do {                                                                                           \
+        ::spg::LaunchScope _scope((kid), (stream_));                                               \
+        ::spg::launch_kernel((kid), kernel, dim3(grid), dim3(block), (size_t)(smem), (stream_), __VA_ARGS__); \
     } while (0)

@@ -39,6 +39,7 @@ struct GemmArgs {
 
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs p) {
+    SPG_PDL_ENTRY();
     __shared__ __align__(16) float As[BK * LDA_S];
     __shared__ __align__(16) float Bs[BK * LDB_S];
     const int t = threadIdx.x;
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs p) {
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const float* __restrict__ ws, int split, int64_t M, int64_t N,
                           const float* __restrict__ bias, float* __restrict__ C, int64_t ldc) {
+    SPG_PDL_ENTRY();
     __shared__ float part[4][64];
     const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
     const int64_t i = (int64_t)blockIdx.x * 64 + x;
@@ -335,6 +337,7 @@ constexpr int kChunkRows = 1024;
 __global__ void __launch_bounds__(256)
 colstats_partial_kernel(const float* __restrict__ Y, int64_t ldy, int64_t M, int C,
                         float* __restrict__ ws) {
+    SPG_PDL_ENTRY();
     __shared__ float s_n[8][32], s_mean[8][32], s_m2[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(1024)
 colstats_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
                       float* __restrict__ mean, float* __restrict__ var,
                       float* __restrict__ out_partials, const FoldArgs f) {
+    SPG_PDL_ENTRY();
     __shared__ double s_a[32][33], s_b[32][33];
     __shared__ double s_mean[32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -505,6 +509,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __re
                                float eps, float* __restrict__ scale, float* __restrict__ shift,
                                float* __restrict__ rmean, float* __restrict__ rvar,
                                long long* __restrict__ nbt, float momentum, float unbias, int C) {
+    SPG_PDL_ENTRY();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt) nbt[0] += 1;
     if (c >= C) return;
@@ -522,6 +527,7 @@ __global__ void __launch_bounds__(256)
 affine_act_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                   const float* __restrict__ shift, int relu, float* __restrict__ out, int64_t ldo,
                   int64_t M, int C) {
+    SPG_PDL_ENTRY();
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     if (c >= C) return;
@@ -536,6 +542,7 @@ affine_act_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restr
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int C,
                       float* __restrict__ ws) {
+    SPG_PDL_ENTRY();
     __shared__ float s[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
@@ -556,6 +563,7 @@ colsum_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int C
 // out[c] = sum over chunks of ws[k*stride + c*inner + off] accumulated in double.
 __global__ void colsum_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
                                     float* __restrict__ out) {
+    SPG_PDL_ENTRY();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double a = 0.0;
@@ -569,6 +577,7 @@ act_bwd_reduce_kernel(const float* __restrict__ G, int64_t ldg, const float* __r
                       const float* __restrict__ shift, const float* __restrict__ mean,
                       const float* __restrict__ var, float eps, int relu, float* __restrict__ ws,
                       int64_t M, int C) {
+    SPG_PDL_ENTRY();
     __shared__ float s1[8][32], s2[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
@@ -602,6 +611,7 @@ act_bwd_reduce_kernel(const float* __restrict__ G, int64_t ldg, const float* __r
 
 __global__ void act_bwd_reduce_final_kernel(const float* __restrict__ ws, int64_t chunks, int C,
                                             float* __restrict__ s1, float* __restrict__ s2) {
+    SPG_PDL_ENTRY();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double a1 = 0.0, a2 = 0.0;
@@ -620,6 +630,7 @@ act_bwd_apply_kernel(const float* __restrict__ G, int64_t ldg, const float* __re
                      int relu, int has_bn, const float* __restrict__ s1,
                      const float* __restrict__ s2, float* __restrict__ dY, int64_t lddy, int64_t M,
                      int C) {
+    SPG_PDL_ENTRY();
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     if (c >= C) return;

@@ -46,6 +46,7 @@ act_bwd_reduce_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* 
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ var, float eps, int relu,
                          float* __restrict__ ws, int64_t M, int C) {
+    SPG_PDL_ENTRY();
     __shared__ float4 s1[8][32], s2[8][32];
     const LaneMap lm = lane_map(C);
     const int x = lm.x, y = threadIdx.x >> 5;
@@ -98,6 +99,7 @@ act_bwd_reduce_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* 
 __global__ void __launch_bounds__(256)
 colsum_v4_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int C,
                  float* __restrict__ ws) {
+    SPG_PDL_ENTRY();
     __shared__ float4 s[8][32];
     const LaneMap lm = lane_map(C);
     const int x = lm.x, y = threadIdx.x >> 5;
@@ -129,6 +131,7 @@ colsum_v4_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int C,
 // out[c] = sum_k ws[k*C + c], one warp per column, fp64 accumulation, fixed order.
 __global__ void __launch_bounds__(128)
 colsum_merge_kernel(const float* __restrict__ ws, int64_t chunks, int C, float* __restrict__ out) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= C) return;
@@ -146,6 +149,7 @@ act_bwd_apply_v4_kernel(const float* __restrict__ G, int64_t ldg, const float* _
                         const float* __restrict__ var, float eps, int relu, int has_bn,
                         const float* __restrict__ s1, const float* __restrict__ s2,
                         float* __restrict__ dY, int64_t lddy, int64_t M, int C) {
+    SPG_PDL_ENTRY();
     const LaneMap lm = lane_map(C);
     const int x = lm.x, y = (threadIdx.x >> 5) * lm.rpw + lm.sub;
     const int rows_per_block = 8 * lm.rpw;
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(256)
 affine_act_v4_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                      const float* __restrict__ shift, int relu, float* __restrict__ out,
                      int64_t ldo, int64_t M, int C) {
+    SPG_PDL_ENTRY();
     const LaneMap lm = lane_map(C);
     const int x = lm.x, y = (threadIdx.x >> 5) * lm.rpw + lm.sub;
     const int rows_per_block = 8 * lm.rpw;

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256)
 ecc_vv_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ w,
                   const int* __restrict__ rowptr, const int* __restrict__ idxn,
                   float4* __restrict__ out, int n_out) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_out) return;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256)
 ecc_mat_fwd_kernel(const float* __restrict__ x, const float4* __restrict__ w,
                    const int* __restrict__ rowptr, const int* __restrict__ idxn,
                    float4* __restrict__ out, int n_out) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_out) return;  // whole warp exits together
@@ -133,6 +135,7 @@ ecc_vv_bwd_w_kernel(const float4* __restrict__ xs, const float4* __restrict__ gs
                     int64_t x_stride4, int64_t g_stride4, int n_iter,
                     const int* __restrict__ rowptr, const int* __restrict__ idxn,
                     float4* __restrict__ grad_w, int n_out, int accumulate) {
+    SPG_PDL_ENTRY();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t node = t / kG;
     const int sub = (int)(t % kG);
@@ -170,6 +173,7 @@ ecc_mat_bwd_w_kernel(const float* __restrict__ xs, const float4* __restrict__ gs
                      int64_t x_stride, int64_t g_stride4, int n_iter,
                      const int* __restrict__ rowptr, const int* __restrict__ idxn,
                      float4* __restrict__ grad_w, int n_out, int accumulate) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_out) return;
@@ -222,6 +226,7 @@ ecc_vv_bwd_x_kernel(const float4* __restrict__ w, const float4* __restrict__ g,
                     const int* __restrict__ src_perm, const int* __restrict__ edge_tgt,
                     const float4* __restrict__ add0, const float4* __restrict__ add1,
                     float4* __restrict__ grad_x, int n_in) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_in) return;
@@ -273,6 +278,7 @@ ecc_mat_bwd_x_kernel(const float4* __restrict__ w, const float4* __restrict__ g,
                      const int* __restrict__ src_perm, const int* __restrict__ edge_tgt,
                      const float* __restrict__ add0, const float* __restrict__ add1,
                      float* __restrict__ grad_x, int n_in) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (node >= n_in) return;
@@ -331,6 +337,7 @@ __global__ void ecc_generic_fwd_kernel(const T* __restrict__ x, const T* __restr
                                        const int* __restrict__ idxn,
                                        const int* __restrict__ idxe, T* __restrict__ out,
                                        int64_t n_out, int c_in, int c_out, int is_mat) {
+    SPG_PDL_ENTRY();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_out * c_out) return;
     const int64_t node = t / c_out;
@@ -365,6 +372,7 @@ __global__ void ecc_generic_bwd_w_kernel(const T* __restrict__ xs, const T* __re
                                          const int* __restrict__ edge_tgt,
                                          T* __restrict__ grad_w, int64_t n_edges, int c_in,
                                          int c_out, int is_mat, int accumulate) {
+    SPG_PDL_ENTRY();
     const int64_t per_edge = is_mat ? (int64_t)c_in * c_out : c_in;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_edges * per_edge) return;
@@ -396,6 +404,7 @@ __global__ void ecc_generic_bwd_x_kernel(const T* __restrict__ w, const T* __res
                                          const int* __restrict__ idxe, const T* __restrict__ add0,
                                          const T* __restrict__ add1, T* __restrict__ grad_x,
                                          int64_t n_in, int c_in, int c_out, int is_mat) {
+    SPG_PDL_ENTRY();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_in * c_in) return;
     const int64_t node = t / c_in;

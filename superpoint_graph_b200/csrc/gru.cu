@@ -185,6 +185,7 @@ gru_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
                const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                const float* __restrict__ w_ig, const float* __restrict__ b_ig,
                float* __restrict__ hy, int64_t n_rows, int H, int flags) {
+    SPG_PDL_ENTRY();
     extern __shared__ float sm[];
     gru_load_weights(sm, w_ih, w_hh, w_ig, H, flags & SPG_GRU_INGATE);
     __syncthreads();
@@ -397,6 +398,7 @@ gru_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
                float* __restrict__ d_gi_out, float* __restrict__ d_gh_out,
                float* __restrict__ d_q_out, float* __restrict__ xprime_out,
                float* __restrict__ dpre_out, int64_t n_rows, int H, int flags) {
+    SPG_PDL_ENTRY();
     extern __shared__ float sm[];
     gru_load_weights(sm, w_ih, w_hh, w_ig, H, flags & SPG_GRU_INGATE);
     __syncthreads();
@@ -459,6 +461,7 @@ rnn_vv_fwd_kernel(float* hs, float* inps, const float4* __restrict__ w,
                   const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                   const float* __restrict__ w_ig, const float* __restrict__ b_ig, int n, int R,
                   int flags, unsigned* barrier) {
+    SPG_PDL_ENTRY();
     extern __shared__ float sm[];
     gru_load_weights(sm, w_ih, w_hh, w_ig, kRecH, flags & SPG_GRU_INGATE);
     __syncthreads();
@@ -522,6 +525,7 @@ rnn_vv_bwd_kernel(const float* __restrict__ hs, const float* __restrict__ inps,
                   float* __restrict__ d_gi, float* __restrict__ d_gh, float* __restrict__ d_q,
                   float* __restrict__ xp, float* dpre, int n, int R, int flags,
                   unsigned* barrier) {
+    SPG_PDL_ENTRY();
     extern __shared__ float sm[];
     gru_load_weights(sm, w_ih, w_hh, w_ig, kRecH, flags & SPG_GRU_INGATE);
     __syncthreads();

@@ -54,6 +54,7 @@ struct CloudBuildArgs {
 constexpr int kCloudWarps = 4;
 
 __global__ void __launch_bounds__(kCloudWarps * 32) cloud_build_kernel(const CloudBuildArgs a, int64_t nv) {
+    SPG_PDL_ENTRY();
     extern __shared__ float sm[];
     const int L = a.L, F = a.F;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,6 +185,7 @@ confusion_count_kernel(const float* __restrict__ logits, int64_t ldl,
                        const int64_t* __restrict__ label_vec, int64_t ldv,
                        unsigned long long* __restrict__ cm, unsigned long long* __restrict__ counters,
                        int64_t* __restrict__ pred_out, int64_t n, int C) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n) return;
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(256)
 nn1_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ qry, int64_t n_q,
            const int64_t* __restrict__ labels_ref, int64_t* __restrict__ labels_out,
            int32_t* __restrict__ idx_out) {
+    SPG_PDL_ENTRY();
     __shared__ double sx[kNnTile], sy[kNnTile], sz[kNnTile];
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double qx = 0.0, qy = 0.0, qz = 0.0;
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(256)
 labels_to_points_kernel(const int64_t* __restrict__ labels_red, const int64_t* __restrict__ comp_ptr,
                         const int64_t* __restrict__ point_ids, int64_t n_comp,
                         uint8_t* __restrict__ labels_full, int64_t n_ver) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= n_comp) return;

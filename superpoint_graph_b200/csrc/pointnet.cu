@@ -18,6 +18,7 @@ constexpr int kPtChunk = 128;
 __global__ void __launch_bounds__(kPtChunk)
 cloud_rows_kernel(const float* __restrict__ clouds, const float* __restrict__ T, int add_eye,
                   float* __restrict__ rows, int64_t ld, int F, int L) {
+    SPG_PDL_ENTRY();
     extern __shared__ float tile[];
     const int64_t b = blockIdx.x;
     const int l0 = blockIdx.y * kPtChunk;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256)
 segmax_fwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                   const float* __restrict__ shift, int relu, float* __restrict__ pooled,
                   int64_t ldp, int* __restrict__ argmax, int L, int C) {
+    SPG_PDL_ENTRY();
     __shared__ float s_v[8][32];
     __shared__ int s_i[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256)
 segmax_fwd_v4_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                      const float* __restrict__ shift, int relu, float* __restrict__ pooled,
                      int64_t ldp, int* __restrict__ argmax, int L, int C) {
+    SPG_PDL_ENTRY();
     __shared__ float4 s_v[8][32];
     __shared__ int4 s_i[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -152,6 +155,7 @@ segmax_fwd_v4_kernel(const float* __restrict__ Y, int64_t ldy, const float* __re
 __global__ void __launch_bounds__(256)
 segmax_bwd_kernel(const float* __restrict__ gp, int64_t ldg, const int* __restrict__ argmax,
                   float* __restrict__ G, int64_t ldG, int64_t rows, int L, int C) {
+    SPG_PDL_ENTRY();
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     if (c >= C) return;
@@ -166,6 +170,7 @@ segmax_bwd_kernel(const float* __restrict__ gp, int64_t ldg, const int* __restri
 __global__ void __launch_bounds__(128)
 stn_apply_bwd_kernel(const float* __restrict__ clouds, const float* __restrict__ dX, int64_t ld,
                      float* __restrict__ dT, int F, int L) {
+    SPG_PDL_ENTRY();
     __shared__ float red[4][4];
     const int64_t b = blockIdx.x;
     const float* xy = clouds + b * (int64_t)F * L;
@@ -205,6 +210,7 @@ segmax_bn_bwd_reduce_kernel(const float* __restrict__ gp, int64_t ldg, const int
                             const float* __restrict__ shift, const float* __restrict__ mean,
                             const float* __restrict__ var, float eps, int relu,
                             float* __restrict__ ws, int64_t B, int L, int C) {
+    SPG_PDL_ENTRY();
     __shared__ float s1[8][32], s2[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
@@ -245,6 +251,7 @@ segmax_bn_bwd_apply_kernel(const float* __restrict__ gp, int64_t ldg, const int*
                            const float* __restrict__ var, float eps, int relu,
                            const float* __restrict__ s1, const float* __restrict__ s2,
                            float* __restrict__ dY, int64_t lddy, int64_t B, int L, int C) {
+    SPG_PDL_ENTRY();
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + x) * 4;
     if (c >= C) return;
@@ -284,6 +291,7 @@ segmax_bn_bwd_apply_kernel(const float* __restrict__ gp, int64_t ldg, const int*
 // out[c] = sum_k ws[k*C + c] in fp64, one warp per column (same as dense_vec.cu's merge).
 __global__ void __launch_bounds__(128)
 pool_colsum_merge_kernel(const float* __restrict__ ws, int64_t chunks, int C, float* __restrict__ out) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= C) return;
@@ -296,6 +304,7 @@ pool_colsum_merge_kernel(const float* __restrict__ ws, int64_t chunks, int C, fl
 
 __global__ void rows_scatter_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                     float* __restrict__ dst, int64_t n, int C) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * C) return;
     const int64_t r = i / C;
@@ -304,6 +313,7 @@ __global__ void rows_scatter_kernel(const float* __restrict__ src, const int64_t
 
 __global__ void rows_gather_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                    float* __restrict__ dst, int64_t n, int C) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * C) return;
     const int64_t r = i / C;
@@ -314,6 +324,7 @@ __global__ void rows_gather_kernel(const float* __restrict__ src, const int64_t*
 // without a transformer): clouds_grad[b, f, l] = rows_grad[b*L + l, f].  grid (B, ceil(L/128)); block 128.
 __global__ void __launch_bounds__(kPtChunk)
 rows_to_clouds_kernel(const float* __restrict__ rows, int64_t ld, float* __restrict__ clouds, int F, int L) {
+    SPG_PDL_ENTRY();
     extern __shared__ float tile[];  // [F][129]
     const int64_t b = blockIdx.x;
     const int l0 = blockIdx.y * kPtChunk;
@@ -341,6 +352,7 @@ __global__ void __launch_bounds__(256)
 segmax_csr_fwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                       const float* __restrict__ shift, int relu, const int64_t* __restrict__ offsets,
                       float* __restrict__ pooled, int64_t ldp, int64_t* __restrict__ argmax, int C) {
+    SPG_PDL_ENTRY();
     __shared__ float s_v[8][32];
     __shared__ long long s_i[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -381,6 +393,7 @@ segmax_csr_fwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __r
 __global__ void __launch_bounds__(256)
 segmax_csr_bwd_kernel(const float* __restrict__ gp, int64_t ldg, const int64_t* __restrict__ argmax,
                       float* __restrict__ G, int64_t ldG, int64_t B, int C) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
     const int64_t b = i / C;
@@ -394,6 +407,7 @@ __global__ void __launch_bounds__(256)
 rows_xy_transform_kernel(const float* __restrict__ in, const float* __restrict__ T, int add_eye,
                          const int32_t* __restrict__ row_seg, float* __restrict__ out, int64_t P,
                          int64_t ld) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P * ld) return;
     const int64_t r = i / ld;
@@ -414,6 +428,7 @@ __global__ void __launch_bounds__(256)
 rows_xy_transform_bwd_kernel(const float* __restrict__ in, int64_t ld, const float* __restrict__ dOut,
                              int64_t ldd, const int64_t* __restrict__ offsets, float* __restrict__ dT,
                              int64_t B) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;

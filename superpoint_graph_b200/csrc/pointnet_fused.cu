@@ -140,6 +140,7 @@ pointnet_fused_kernel(const PfArgs p, const __grid_constant__ CUtensorMap wmap,
                          smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    SPG_PDL_ENTRY();  // set-up above overlaps the previous kernel of the stream; global memory only below
     for (int i = t; i < p.n_bias; i += PF_THREADS) bias_s[i] = p.bias[i];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -385,6 +386,7 @@ pointnet_fused_bf16_kernel(const PfArgs p, const __grid_constant__ CUtensorMap w
                          smem_u32(&tmem_base_s)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    SPG_PDL_ENTRY();  // set-up above overlaps the previous kernel of the stream; global memory only below
     for (int i = t; i < p.n_bias; i += PF_THREADS) bias_s[i] = p.bias[i];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -547,6 +549,7 @@ pointnet_fused_bf16_kernel(const PfArgs p, const __grid_constant__ CUtensorMap w
 __global__ void pack_weights_bf16_kernel(const float* __restrict__ W, int64_t ldw,
                                          const float* __restrict__ row_scale, int N, int K, int k_valid,
                                          uint16_t* __restrict__ img) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     const int n = (int)(i / K), k = (int)(i % K);

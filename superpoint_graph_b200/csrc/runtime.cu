@@ -3,6 +3,8 @@
 #include <mutex>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace spg {
@@ -45,6 +47,23 @@ static cudaEvent_t get_event() {
     return e;
 }
 
+static std::atomic<int> g_pdl{-1};  // -1: read SPG_PDL from the environment on first use (default on)
+
+// mode 0: off; 1: every kernel; 2: every kernel except the persistent tensor-core kernels; 3: only the
+// tcgen05 GEMM and its merge companion
+bool pdl_enabled(int kid) {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SPG_PDL");
+        v = e ? atoi(e) : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    const bool big = kid == K_TC_GEMM || kid == K_TC_DW || kid == K_POINTNET_FUSED;
+    if (v == 2) return !big;
+    if (v == 3) return kid == K_TC_GEMM || kid == K_TC_MERGE;
+    return v != 0;
+}
+
 LaunchScope::LaunchScope(int kernel_id, cudaStream_t s) : kid(kernel_id), stream(s), slot(-1) {
     g_launches[kid].fetch_add(1, std::memory_order_relaxed);
     if (g_enabled.load(std::memory_order_relaxed)) {
@@ -73,6 +92,11 @@ using namespace spg;
 extern "C" {
 
 int spg_version(void) { return 100; }
+
+int spg_set_pdl(int enabled) {
+    g_pdl.store(enabled < 0 ? 0 : enabled, std::memory_order_relaxed);
+    return SPG_OK;
+}
 
 const char* spg_error_string(int code) {
     if (code == SPG_OK) return "ok";

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
                const float* __restrict__ cw, int64_t ignore_index, double* __restrict__ acc,
                float* __restrict__ dlogits, int64_t n, int C) {
+    SPG_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
@@ -46,6 +47,7 @@ ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ tar
 
 __global__ void ce_loss_final_kernel(const double* __restrict__ acc, float* __restrict__ loss,
                                      float* __restrict__ dlogits, int64_t total) {
+    SPG_PDL_ENTRY();
     const double wsum = acc[1];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) loss[0] = (float)(acc[0] / wsum);  // 0/0 = NaN for an all-ignored batch, as torch
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(256)
 clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                   float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                   float wd, float clip, float gscale, float bc1, float bc2_sqrt) {
+    SPG_PDL_ENTRY();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(256)
 clamp_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                       float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                       float wd, float clip, float gscale, const long long* __restrict__ counter) {
+    SPG_PDL_ENTRY();
     const double step = (double)(counter[0] + 1);
     const float bc1 = (float)(1.0 - pow((double)b1, step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
@@ -99,7 +103,8 @@ clamp_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     }
 }
 
-__global__ void counter_increment_kernel(long long* counter) { counter[0] += 1; }
+__global__ void counter_increment_kernel(long long* counter) {
+    SPG_PDL_ENTRY(); counter[0] += 1; }
 
 // ---- the step's only collective, fused with what follows it (main.py:210-213) ----------
 // One-shot all-reduce over NVLink peer memory + average + element-wise clamp + Adam in ONE kernel:
@@ -127,6 +132,7 @@ allreduce_clamp_adam_kernel(const float* const* __restrict__ peer_grads, unsigne
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
                             float clip, float gscale, long long* __restrict__ counter,
                             unsigned* __restrict__ epoch_ptr, unsigned* __restrict__ ticket) {
+    SPG_PDL_ENTRY();
     const unsigned epoch = epoch_ptr[0] + 1u;
     const unsigned nb = gridDim.x;
     unsigned* my_flags = peer_flags[rank];

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const DwArgs p) {
             reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
     }
+    SPG_PDL_ENTRY();  // set-up above overlaps the previous kernel of the stream; global memory only below
 
     const int64_t m_beg = (int64_t)blockIdx.x * p.pts_per_cta;
     const int64_t m_end = min(p.M, m_beg + p.pts_per_cta);

@@ -152,13 +152,7 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
         mbar_init(bar_accempty(1), T2_EPI_WARPS);
         mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // resident weight slice by TMA: rows [n0, n0+NS) of every (chunk, hi|lo) block of the image
-        // (a block is [N rows][128 B], already in the SWIZZLE_128B layout the MMA reads)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
-        mbar_expect_tx(bar_w, (uint32_t)(nk * 2 * NS * T2_KC * 4));
-        const uint32_t wres_u = smem_u32(wres);
-        for (int blk = 0; blk < nk * 2; ++blk)
-            tma_load_2d(wres_u + (uint32_t)blk * (NS * T2_KC * 4), &wmap, 0, blk * p.N + n0, bar_w);
     }
     if (warp == 0) {
         __syncwarp();
@@ -167,6 +161,17 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
                      "r"((uint32_t)(2 * NS < 32 ? 32 : 2 * NS))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Everything above (barrier init, descriptor prefetch, tensor-memory allocation) overlaps the previous
+    // kernel of the stream; nothing below this line runs before that kernel's results are visible.
+    SPG_PDL_ENTRY();
+    if (t == 0) {
+        // resident weight slice by TMA: rows [n0, n0+NS) of every (chunk, hi|lo) block of the image
+        // (a block is [N rows][128 B], already in the SWIZZLE_128B layout the MMA reads)
+        mbar_expect_tx(bar_w, (uint32_t)(nk * 2 * NS * T2_KC * 4));
+        const uint32_t wres_u = smem_u32(wres);
+        for (int blk = 0; blk < nk * 2; ++blk)
+            tma_load_2d(wres_u + (uint32_t)blk * (NS * T2_KC * 4), &wmap, 0, blk * p.N + n0, bar_w);
     }
     // Producer threads put their first A chunks in flight before anything else: the global-load
     // latency then overlaps the resident-weight load and the CTA-wide barrier below.
@@ -541,6 +546,7 @@ tc_gemm2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap wmap) {
 // WHOLE grid fits on the GPU and thereby serialises against the weight-gradient kernels of the side
 // stream — 2.30 ms per step instead of 1.97.)
 __global__ void __launch_bounds__(256) tc_merge_kernel(const Tc2Args p, int P) {
+    SPG_PDL_ENTRY();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 8 + warp;
     if (c >= p.N) return;

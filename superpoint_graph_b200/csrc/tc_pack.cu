@@ -16,6 +16,7 @@ constexpr int TC_KC = 32;       // floats per K chunk (128 B swizzle row)
 // transpose=1: B[n][k] = W[k*ldw + n] (the data-gradient GEMM consumes W^T).
 __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int64_t ldw, int transpose,
                                        int N, int K, int k_valid, float* __restrict__ img) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     const int n = (int)(i / K), k = (int)(i % K);
@@ -35,6 +36,7 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int64_t ldw,
 __global__ void tc_pack_weights_scaled_kernel(const float* __restrict__ W, int64_t ldw,
                                               const float* __restrict__ row_scale, int N, int K, int k_valid,
                                               float* __restrict__ img) {
+    SPG_PDL_ENTRY();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     const int n = (int)(i / K), k = (int)(i % K);
@@ -54,6 +56,7 @@ __global__ void tc_pack_weights_scaled_kernel(const float* __restrict__ W, int64
 // image, first element index of job j}; a thread finds its job by a linear scan (<= 64 jobs).
 __global__ void tc_pack_weights_multi_kernel(const long long* __restrict__ table, int n_jobs,
                                              long long total) {
+    SPG_PDL_ENTRY();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int j = 0;

@@ -306,6 +306,16 @@ USE_TC = [os.environ.get("SPG_TC", "1") != "0"]  # tcgen05 path for the large po
 USE_FUSED_RNN = [os.environ.get("SPG_FUSED_RNN", "1") != "0"]  # one-kernel R x {ECC, cell} loop
 USE_FUSED_BNBWD = [os.environ.get("SPG_FUSED_BNBWD", "1") != "0"]  # BatchNorm backward inside the dX GEMM (prologue + epilogue sums)
 USE_FUSED_EVAL = [os.environ.get("SPG_FUSED_EVAL", "1") != "0"]  # eval-mode PointNet trunk as one kernel per chain
+def set_pdl(mode):
+    """Programmatic dependent launch policy of the library (spg_set_pdl): 1 = every kernel is scheduled while
+    its predecessor on the stream still runs and waits on the device for it (measured -1.5 ... -4.5 % on the
+    single-stream inference workloads), 0 = plain stream order (the two-stream training schedule is 2 % faster
+    that way: early-resident GEMM CTAs take SMs from the weight-gradient stream).  An explicit SPG_PDL in the
+    environment wins."""
+    if "SPG_PDL" not in os.environ:
+        _lib.call("spg_set_pdl", int(mode))
+
+
 USE_SIDE_STREAM = [os.environ.get("SPG_SIDE_STREAM", "1") != "0"]  # Trainer: block-local weight gradients on a 2nd stream
 
 

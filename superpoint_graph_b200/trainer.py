@@ -164,6 +164,13 @@ class Trainer(object):
     def compute_gradients(self, db):
         """Forward, loss, backward; gathers every parameter gradient into the flat buffer.
         Returns (loss[1], logits).  Purely local to this rank (no collective)."""
+        ops.set_pdl(0 if self._side is not None else 1)  # launch policy measured per schedule, see ops.set_pdl
+        try:
+            return self._compute_gradients(db)
+        finally:
+            ops.set_pdl(1)
+
+    def _compute_gradients(self, db):
         if self.dtype != "f32":
             raise NotImplementedError("training runs in fp32 (3xTF32 on the tensor cores); bf16 arithmetic is "
                                       "implemented for the inference forward only (Trainer.eval_step)")
