@@ -638,6 +638,8 @@ def run_b200(args):
         if graph_keys is not None:  # refresh the graph's static input buffers, then replay
             hbs[i % nb].copy_into(dbs[i % nb])
             return trainer.replay(graph_keys[i % nb])
+        if not train:  # inference: chunked upload overlapped with the forward (Trainer.eval_step_host)
+            return None, trainer.eval_step_host(hbs[i % nb])
         return step(hbs[i % nb].to_device(dev))
 
     for i in range(0 if args.no_e2e else max(3, args.warmup // 2)):

@@ -365,6 +365,20 @@ int spg_cloud_build(const float* points, int64_t ldp, const int64_t* sp_start,
                     int n_attribs, int n_points, int normalize, const double* xform,
                     const float* jitter, float jitter_sigma, float jitter_clip, int64_t seed,
                     float* clouds, float* diameters, int64_t n_clouds, spg_stream_t stream);
+/* Device-side builder of the graph views the ECC kernels read, from the collated (idxn, degs) pair of
+ * ref: learning/ecc/GraphConvInfo.py:48-69 (set_batch leaves idxn = source node per edge with the edges
+ * sorted by target, degs = in-degree per target; the reference uploads both, GraphConvInfo.py:71-77):
+ *   idxn32 [E] = int32(idxn); tgt_rowptr [n_out+1] = exclusive scan of degs; edge_tgt [E] = target of each
+ *   edge; src_perm [E] = the STABLE permutation sorting the edges by source (identical to numpy
+ *   argsort(kind="stable")); src_rowptr [n_in+1] = first position of each source in that order.
+ * status [1] (device int32) receives a bit mask: 1 = idxn out of [0,n_in), 2 = a degree out of range,
+ * 4 = sum(degs) != E; the outputs are undefined when it is non-zero.  workspace: 256-byte aligned,
+ * spg_graph_build_workspace() bytes.  All int64 inputs and int32 outputs are device pointers.           */
+int spg_graph_build_workspace(int64_t n_out, int64_t n_in, int64_t n_edges, int64_t* bytes);
+int spg_graph_build(const int64_t* idxn, const int64_t* degs, int64_t n_out, int64_t n_in, int64_t n_edges,
+                    int32_t* idxn32, int32_t* tgt_rowptr, int32_t* edge_tgt, int32_t* src_rowptr,
+                    int32_t* src_perm, int32_t* status, void* workspace, int64_t workspace_bytes,
+                    spg_stream_t stream);
 /* Evaluation bookkeeping (ref: learning/main.py:257-262,297-305 + metrics.py:16-18):
  * pred_i = first argmax of logits[i,:]; for nodes with label_mode[i] != -100:
  * confusion[:, pred_i] += label_vec[i,:], counters[0] += 1, counters[1] += (pred_i == label_mode[i]).

@@ -49,6 +49,7 @@ enum KernelId {
     K_CONFUSION,
     K_TC_MERGE,
     K_POINTNET_FUSED,
+    K_GRAPH_BUILD,
     K_COUNT
 };
 

@@ -20,7 +20,7 @@ static const char* kKernelNames[K_COUNT] = {
     "ce_loss",           "ce_loss_final",      "clamp_adam",          "tc_gemm_3xtf32",
     "tc_pack_weights",     "tc_dw_3xtf32",       "rnn_ecc_gru_fwd",     "rnn_ecc_gru_bwd",
     "cloud_build",       "confusion_count",    "tc_merge",
-    "pointnet_fused_eval",
+    "pointnet_fused_eval", "graph_build",
 };
 
 struct Record {

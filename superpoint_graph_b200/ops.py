@@ -91,14 +91,65 @@ class EccGraph(object):
         self.idxe_host = None if idxe is None else idxe.detach().cpu().numpy().astype(np.int32)
         self._dev = {}
 
+    GRAPH_FIELDS = ("tgt_rowptr", "idxn", "edge_tgt", "src_rowptr", "src_perm")
+
+    @classmethod
+    def from_device(cls, idxn, degs, n_in=None, check=True, idxe=None):
+        """Builds the views ON THE DEVICE from the reference's collated pair (int64 CUDA tensors, as
+        GraphConvInfo.cuda() holds them, GraphConvInfo.py:71-77) — spg_graph_build: a scan, a stable radix
+        sort and three small kernels instead of host numpy; bit-identical to the host builder.
+        check=True reads the device status word back (one synchronisation) and raises like the host
+        builder does; callers that validated the host arrays already pass check=False."""
+        _need_cuda(idxn, degs)
+        g = cls.__new__(cls)
+        g.n_out, g.n_edges = int(degs.numel()), int(idxn.numel())
+        g.n_in = int(n_in if n_in is not None else g.n_out)
+        g.host, g.idxe_host = None, None
+        dev = graph_build_alloc(g.n_out, g.n_in, g.n_edges, idxn.device)
+        graph_build_into(dev, idxn, degs, g.n_in)
+        if idxe is not None:
+            dev["idxe"] = idxe.to(device=idxn.device, dtype=torch.int32)
+        if check:
+            st = int(dev["status"].item())
+            if st:
+                raise ValueError("graph build rejected the arrays (status %d: 1 = idxn out of range, "
+                                 "2 = bad degree, 4 = sum(degs) != number of edges)" % st)
+        g._dev = {(idxn.device.type, idxn.device.index): dev}
+        return g
+
     def to(self, device):
         device = torch.device(device)
         key = (device.type, device.index)
         if key not in self._dev:
+            if self.host is None:
+                raise RuntimeError("this graph was built on %s; it has no host copy to move" % (list(self._dev),))
             d = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
             d["idxe"] = None if self.idxe_host is None else torch.from_numpy(self.idxe_host).to(device)
             self._dev[key] = d
         return self._dev[key]
+
+
+def graph_build_alloc(n_out, n_in, n_edges, device):
+    """Output tensors + status word + workspace of spg_graph_build (static addresses: a captured CUDA graph
+    reads them, HostBatch.copy_into rebuilds into them)."""
+    nbytes = torch.zeros(1, dtype=torch.int64)
+    _lib.call("spg_graph_build_workspace", n_out, n_in, n_edges, nbytes)
+    i32 = dict(dtype=torch.int32, device=device)
+    return {"tgt_rowptr": torch.empty(n_out + 1, **i32), "idxn": torch.empty(n_edges, **i32),
+            "edge_tgt": torch.empty(n_edges, **i32), "src_rowptr": torch.empty(n_in + 1, **i32),
+            "src_perm": torch.empty(n_edges, **i32), "idxe": None, "status": torch.zeros(1, **i32),
+            "_ws": torch.empty(int(nbytes[0]) + 256, dtype=torch.uint8, device=device)}
+
+
+def graph_build_into(dev, idxn, degs, n_in):
+    """Runs spg_graph_build on the current stream into the tensors of graph_build_alloc()."""
+    _need_cuda(idxn, degs)
+    assert idxn.dtype == torch.int64 and degs.dtype == torch.int64 and idxn.is_contiguous() and degs.is_contiguous()
+    ws = dev["_ws"]
+    off = (-ws.data_ptr()) % 256
+    _lib.call("spg_graph_build", idxn, degs, degs.numel(), int(n_in), idxn.numel(), dev["idxn"], dev["tgt_rowptr"],
+              dev["edge_tgt"], dev["src_rowptr"], dev["src_perm"], dev["status"], ws.data_ptr() + off,
+              ws.numel() - off, _lib.current_stream())
 
 
 def build_csr_host(idxn, degs, n_in):

@@ -87,14 +87,19 @@ class GraphConvInfo(object):
         return self._graph
 
     def cuda(self):
-        g = self.graph()
+        """Uploads the buffers (GraphConvInfo.py:71-77) and builds the kernels' CSR views on the device from
+        the uploaded (idxn, degs) pair (spg_graph_build) unless a host-built graph exists already."""
         self._idxn = self._idxn.cuda()
         if self._idxe is not None:
             self._idxe = self._idxe.cuda()
         self._degrees_gpu = self._degrees.cuda()
         self._edgefeats = self._edgefeats.cuda()
         self._edge_indexes = self._edge_indexes.cuda()
-        g.to(self._idxn.device)
+        if self._graph is None:
+            self._graph = ops.EccGraph.from_device(self._idxn, self._degrees_gpu, n_in=int(self._degrees.numel()),
+                                                   idxe=self._idxe, check=True)
+        else:
+            self._graph.to(self._idxn.device)
 
     def get_buffers(self):
         return self._idxn, self._idxe, self._degrees, self._degrees_gpu, self._edgefeats
@@ -103,13 +108,20 @@ class GraphConvInfo(object):
         return self._edge_indexes
 
 
-def _graph_for(idxn, idxe, degs, n_in):
-    """EccGraph for a raw (idxn, idxe, degs) triple, cached on the degs tensor object."""
+def _graph_for(idxn, idxe, degs, degs_gpu, n_in):
+    """EccGraph for a raw (idxn, idxe, degs, degs_gpu) argument list, cached on the degs tensor object and
+    keyed on the identity AND version of the index tensors (an in-place edit invalidates it).  CUDA
+    arguments are turned into the CSR views on the device; host arguments by the numpy builder."""
     cache = getattr(degs, "_spg_graph", None)
-    key = (idxn.data_ptr(), None if idxe is None else idxe.data_ptr(), int(idxn.numel()), n_in)
+    key = (idxn.data_ptr(), idxn._version, None if idxe is None else (idxe.data_ptr(), idxe._version),
+           degs._version, int(idxn.numel()), n_in)
     if cache is not None and cache[0] == key:
         return cache[1]
-    g = ops.EccGraph(idxn, idxe, degs, n_in=n_in)
+    if idxn.is_cuda and degs_gpu is not None and degs_gpu.is_cuda:
+        g = ops.EccGraph.from_device(idxn.long().contiguous(), degs_gpu.long().contiguous(), n_in=n_in,
+                                     idxe=idxe, check=True)
+    else:
+        g = ops.EccGraph(idxn, idxe, degs, n_in=n_in)
     try:
         degs._spg_graph = (key, g)
     except Exception:
@@ -126,7 +138,7 @@ class GraphConvFunction(torch.autograd.Function):
                 edge_mem_limit=1e20):
         full = weights.dim() == 3
         assert full or (in_channels == out_channels and weights.size(1) == in_channels)
-        graph = idxn if isinstance(idxn, ops.EccGraph) else _graph_for(idxn, idxe, degs,
+        graph = idxn if isinstance(idxn, ops.EccGraph) else _graph_for(idxn, idxe, degs, degs_gpu,
                                                                        int(input.shape[0]))
         ctx.save_for_backward(input, weights)
         ctx._graph = graph

@@ -150,18 +150,23 @@ class RNNGraphConvModule(nn.Module):
         self._gci = gc_info
         self._prefetched = None
 
-    def prefetch_filters(self):
-        """Trainer only (needs ops.SIDE): evaluate the filter network now, on the side stream —
-        it depends on the edge features alone, so it can run underneath the PointNet forward
-        instead of after it.  forward() picks the result up and joins the stream."""
-        side = ops.SIDE[0]
-        if side is None or self._gci is None:
+    def prefetch_filters(self, inline=False):
+        """Evaluate the filter network now — it depends on the edge features alone.  Trainer (ops.SIDE
+        installed): on the side stream, underneath the PointNet forward; forward() picks the result up and
+        joins the stream.  inline=True: on the current stream (the pipelined inference path runs it while
+        the point clouds are still being uploaded)."""
+        side = None if inline else ops.SIDE[0]
+        if (side is None and not inline) or self._gci is None:
             return
         edgefeats = self._gci.get_buffers()[4]
         fspecs, fparams = parse_sequential(self._fnet, self.training)
+        if side is None:
+            self._prefetched = (self._gci, self.training, False) + _filter_bank(edgefeats, fspecs, fparams,
+                                                                                self.training)
+            return
         with side.fork(edgefeats):
-            self._prefetched = (self._gci, self.training) + _filter_bank(edgefeats, fspecs, fparams,
-                                                                         self.training)
+            self._prefetched = (self._gci, self.training, True) + _filter_bank(edgefeats, fspecs, fparams,
+                                                                               self.training)
 
     def forward(self, hx):
         idxn, idxe, degs, degs_gpu, edgefeats = self._gci.get_buffers()
@@ -171,10 +176,11 @@ class RNNGraphConvModule(nn.Module):
         cparams = [q for q in cell.cell_params() if q is not None]
         pre, self._prefetched = self._prefetched, None
         if pre is not None:
-            if pre[0] is not self._gci or pre[1] != self.training or ops.SIDE[0] is None:
+            if pre[0] is not self._gci or pre[1] != self.training or (pre[2] and ops.SIDE[0] is None):
                 raise RuntimeError("prefetch_filters() result does not belong to this forward")
-            ops.SIDE[0].join()
-            pre = pre[2:]
+            if pre[2]:
+                ops.SIDE[0].join()
+            pre = pre[3:]
         return _RecurrentECCFunction.apply(hx, edgefeats, graph, fspecs, len(fparams), cell.flags(),
                                            self._nrepeats, self._cat_all, self.training, pre,
                                            *(fparams + cparams))

@@ -6,6 +6,7 @@ with the model's parameters living in ONE flat fp32 buffer so that the gradient 
 single NCCL call and clamp+Adam a single kernel (scene-parallel data parallelism: every rank
 owns whole scenes, the graph never crosses devices).
 """
+import copy
 from types import SimpleNamespace
 
 import torch
@@ -59,9 +60,11 @@ def flatten_parameters(model):
 
 class HostBatch(object):
     """One collated batch in pinned host memory, in the layout the reference's collate produces
-    (learning/spg.py:178-193) plus the host-built CSR views of the graph."""
+    (learning/spg.py:178-193): clouds, global features, edge features, labels and the (idxn, degs) pair of
+    GraphConvInfo.set_batch.  The CSR views the kernels read are built ON THE DEVICE from that pair on every
+    upload (ops.graph_build_into -> spg_graph_build), inside the timed end-to-end region."""
 
-    FIELDS = ("clouds", "clouds_global", "edgefeats", "labels", "idx_valid")
+    FIELDS = ("clouds", "clouds_global", "edgefeats", "labels", "idx_valid", "idxn", "degs")
 
     def __init__(self, batch):
         self.n_nodes = int(batch["degs"].numel())
@@ -71,44 +74,44 @@ class HostBatch(object):
         self.clouds_global = batch["clouds_global"]
         self.edgefeats = batch["edgefeats"]
         self.labels = batch["labels"]
-        self.gi = GraphConvInfo.from_arrays(batch["idxn"], batch["degs"], batch["edgefeats"])
-        self.graph_host = self.gi.graph().host
+        self.idxn = torch.as_tensor(batch["idxn"], dtype=torch.long).contiguous()
+        self.degs = torch.as_tensor(batch["degs"], dtype=torch.long).contiguous()
+        # the checks of the host builder (ops.EccGraph.__init__), once per batch on the host arrays: the
+        # device builder then runs without reading its status word back
+        if int(self.degs.sum()) != self.idxn.numel() or (self.degs.numel() and int(self.degs.min()) < 0):
+            raise ValueError("sum(degs)=%d does not match the number of edges %d"
+                             % (int(self.degs.sum()), self.idxn.numel()))
+        if self.idxn.numel() and (int(self.idxn.min()) < 0 or int(self.idxn.max()) >= self.n_nodes):
+            raise ValueError("idxn out of range")
+        self.gi = GraphConvInfo.from_arrays(self.idxn, self.degs, self.edgefeats)
         if torch.cuda.is_available():
             for f in self.FIELDS:
                 setattr(self, f, getattr(self, f).pin_memory())
-            self.graph_pinned = {k: torch.from_numpy(v).pin_memory() for k, v in self.graph_host.items()}
-        else:
-            self.graph_pinned = {k: torch.from_numpy(v) for k, v in self.graph_host.items()}
 
     def h2d_bytes(self):
-        n = sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
-        n += sum(v.numel() * v.element_size() for v in self.graph_pinned.values())
-        return int(n)
+        return int(sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS))
 
-    def to_device(self, device):
-        """Asynchronous copies on the current stream; returns a DeviceBatch."""
+    def to_device(self, device, skip=()):
+        """Asynchronous copies + the device graph build on the current stream; returns a DeviceBatch.
+        Fields named in `skip` stay on the host (Trainer.eval_step_host uploads the clouds itself)."""
+        device = torch.device(device)
         d = DeviceBatch()
         for f in self.FIELDS:
-            setattr(d, f, getattr(self, f).to(device, non_blocking=True))
-        g = self.gi.graph()
-        key = (device.type, device.index)
-        dev = {k: v.to(device, non_blocking=True) for k, v in self.graph_pinned.items()}
-        dev["idxe"] = None
-        g._dev[key] = dev  # the kernels read the graph through EccGraph.to(device)
-        d.gi = self.gi
+            setattr(d, f, getattr(self, f) if f in skip else getattr(self, f).to(device, non_blocking=True))
+        g = ops.EccGraph.from_device(d.idxn, d.degs, n_in=self.n_nodes, check=False)
+        d.gi = copy.copy(self.gi)  # (shallow: one GraphConvInfo per device batch, sharing the host arrays)
+        d.gi._graph = g  # the kernels read the graph through GraphConvInfo.graph().to(device)
         d.gi._edgefeats = d.edgefeats
         d.n_nodes = self.n_nodes
         return d
 
-
     def copy_into(self, d):
         """Asynchronous H2D refresh of an existing DeviceBatch of the same shapes (static buffers of a
-        captured CUDA graph)."""
+        captured CUDA graph), and the rebuild of its graph views in place."""
         for f in self.FIELDS:
             getattr(d, f).copy_(getattr(self, f), non_blocking=True)
         dev = d.gi.graph()._dev[(d.clouds.device.type, d.clouds.device.index)]
-        for k, v in self.graph_pinned.items():
-            dev[k].copy_(v, non_blocking=True)
+        ops.graph_build_into(dev, d.idxn, d.degs, self.n_nodes)
 
 
 class DeviceBatch(object):
@@ -292,6 +295,32 @@ class Trainer(object):
         ops.EVAL_BF16[0] = self.dtype == "bf16"
         try:
             return self.forward(db)
+        finally:
+            ops.EVAL_BF16[0] = False
+
+    @torch.no_grad()
+    def eval_step_host(self, hb):
+        """Inference straight from a pinned HostBatch: the small arrays go up first, the graph views are built
+        on the device, the point clouds follow in chunks on a copy stream while the filter networks and the
+        PointNet of the chunks already there run (CloudEmbedder.run_pipelined).  Same result as
+        eval_step(hb.to_device(dev)) up to the per-row summation order of the FC layers."""
+        self.model.eval()
+        ops.EVAL_BF16[0] = self.dtype == "bf16"
+        try:
+            dev = self.flat.device
+            if hb.clouds.numel() * hb.clouds.element_size() < CloudEmbedder.PIPELINE_MIN_BYTES:
+                return self.forward(hb.to_device(dev))
+            d = hb.to_device(dev, skip=("clouds", "clouds_global"))
+            self.model.ecc.gconvs[0].set_info(d.gi)
+
+            def filters():
+                for gc in self.model.ecc.gconvs:
+                    if hasattr(gc, "prefetch_filters"):
+                        gc.prefetch_filters(inline=True)
+
+            emb = self.embedder.run_pipelined(self.model, hb.clouds, hb.clouds_global, d.idx_valid, d.n_nodes,
+                                              overlap=filters)
+            return self.model.ecc(emb)
         finally:
             ops.EVAL_BF16[0] = False
 

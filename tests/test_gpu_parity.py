@@ -782,3 +782,61 @@ def test_side_stream_gives_identical_steps(dev, monkeypatch, graph):
     (l_a, p_a, o_a, g_a), (l_b, p_b, o_b, g_b) = results
     assert l_a == l_b
     assert torch.equal(g_a, g_b) and torch.equal(p_a, p_b) and torch.equal(o_a, o_b)
+
+
+# ------------------------------------------------------------------ device-side graph build (f1)
+@pytest.mark.parametrize("n,deg,seed", [(1, 0, 0), (7, 3, 1), (1024, 9, 2), (20000, 12, 3), (200000, 9, 4)])
+def test_graph_build_device_is_bit_identical_to_host_builder(dev, n, deg, seed):
+    """spg_graph_build (scan + stable radix sort + 3 kernels) against the numpy builder the CPU tests pin
+    (tests/test_host_logic.py): every view bit-exact, including the order of equal sources in src_perm."""
+    from superpoint_graph_b200 import ops
+    rng = np.random.RandomState(seed)
+    degs = rng.randint(0, 2 * deg + 1, size=n).astype(np.int64) if deg else np.zeros(n, dtype=np.int64)
+    if n > 3:
+        degs[rng.randint(0, n, size=max(1, n // 50))] = 0   # isolated targets
+        degs[rng.randint(0, n)] = 40 * max(deg, 1)           # one hub
+    E = int(degs.sum())
+    idxn = rng.randint(0, n, size=E).astype(np.int64)
+    if E > 10:
+        idxn[: E // 4] = idxn[0]                              # many equal keys: stability matters
+    want = ops.build_csr_host(idxn, degs, n)
+    g = ops.EccGraph.from_device(t(idxn, dev), t(degs, dev), n_in=n, check=True)
+    got = g.to(dev)
+    for k in ops.EccGraph.GRAPH_FIELDS:
+        assert got[k].dtype == torch.int32
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    assert int(got["status"].item()) == 0
+
+
+def test_graph_build_device_rejects_bad_arrays(dev):
+    from superpoint_graph_b200 import ops
+    degs = torch.tensor([2, 1, 0], dtype=torch.int64, device=dev)
+    with pytest.raises(ValueError, match="status 1"):
+        ops.EccGraph.from_device(torch.tensor([0, 3, 1], dtype=torch.int64, device=dev), degs, n_in=3)
+    with pytest.raises(ValueError, match="status 4"):
+        ops.EccGraph.from_device(torch.tensor([0, 1], dtype=torch.int64, device=dev), degs, n_in=3)
+
+
+def test_graphconvinfo_cuda_builds_on_device_and_matches_golden(golden_dir, dev):
+    """GraphConvInfo.cuda() (the call learning/main.py makes through set_info) now derives the CSR views on
+    the device; the convolution through it must equal the one through the host-built graph."""
+    from superpoint_graph_b200 import ops
+    from superpoint_graph_b200.spg_ecc import GraphConvFunction, GraphConvInfo
+    rng = np.random.RandomState(5)
+    n = 500
+    degs = rng.randint(0, 12, size=n).astype(np.int64)
+    idxn = rng.randint(0, n, size=int(degs.sum())).astype(np.int64)
+    ef = rng.randn(idxn.shape[0], 13).astype(np.float32)
+    gi = GraphConvInfo.from_arrays(idxn, degs, ef)
+    gi.cuda()
+    assert gi.graph().host is None  # built on the device
+    x = torch.randn(n, 32, device=dev)
+    w = torch.randn(idxn.shape[0], 32, device=dev)
+    a = GraphConvFunction.apply(x, w, 32, 32, gi.graph(), None, None, None)
+    host = ops.EccGraph(t(idxn), None, t(degs), n_in=n)
+    b = GraphConvFunction.apply(x, w, 32, 32, host, None, None, None)
+    assert torch.equal(a, b)
+    # raw reference-style argument list with CUDA tensors: cached device build
+    bufs = gi.get_buffers()
+    c = GraphConvFunction.apply(x, w, 32, 32, bufs[0], bufs[1], bufs[2], bufs[3])
+    assert torch.equal(a, c)

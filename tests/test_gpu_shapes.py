@@ -254,9 +254,17 @@ def test_sema3d_eval_chunked_vs_oracle(dev, monkeypatch):
     with torch.no_grad():
         want = nets_ref.spg_forward(_f64(batch), sd_ptn, sd_ecc, pcfg, mcfg, False)
     monkeypatch.setattr(spg_pointnet, "_EVAL_CHUNK", 1024)
-    got = tr.eval_step(HostBatch(batch).to_device(dev))
+    hb = HostBatch(batch)
+    got = tr.eval_step(hb.to_device(dev))
     assert got.shape == (3000, 8)
     close(got, want, 1e-4)
+    # the pipelined upload (chunks on a copy stream, PointNet per chunk, filter networks underneath) is the
+    # same forward: 3000 x 11 x 128 floats = 16.9 MB, above CloudEmbedder.PIPELINE_MIN_BYTES
+    assert hb.clouds.numel() * 4 >= spg_pointnet.CloudEmbedder.PIPELINE_MIN_BYTES
+    for _ in range(2):  # second call: the copy stream and the allocator's blocks are reused
+        piped = tr.eval_step_host(hb)
+        close(piped, want, 1e-4)
+        close(piped, got, 1e-5)
 
 
 def test_vkitti_widths_train_step_vs_oracle(dev):
