@@ -503,6 +503,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from superpoint_graph_b200 import _lib, ops, workloads
+    from superpoint_graph_b200.spg_pointnet import CloudEmbedder
     from superpoint_graph_b200.trainer import HostBatch, Trainer, create_model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -628,6 +629,43 @@ def run_b200(args):
             value = all_units / (total_ms * 1e-3)
         except Exception as ex:  # keep the eager numbers
             graph_keys, graph_err = None, repr(ex)
+    eval_keys = None
+    if not args.no_graph and not train and w["nodes"] <= 50000:
+        # inference: the same forward replayed from a CUDA graph (the eager forward is issue-bound on the host
+        # at these sizes)
+        try:
+            per_step0 = ops.total_launches()
+            eval_keys = [trainer.capture_eval(dbs[i], key=i, warmup=1) for i in range(nb)]
+            launches_per_step = (ops.total_launches() - per_step0) // (2 * nb)
+            for i in range(args.warmup):
+                trainer.replay_eval(eval_keys[i % nb])
+            barrier()
+            sampler = ClockSampler(local)
+            sampler.start()
+            evs, done_units = [], 0
+            t_wall = time.perf_counter()
+            for i in range(args.steps):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                trainer.replay_eval(eval_keys[i % nb])
+                e.record()
+                evs.append((s, e))
+                done_units += units[i % nb]
+            barrier()
+            wall = time.perf_counter() - t_wall
+            clocks = sampler.stop()
+            launches = launches_per_step * args.steps
+            total_ms = sum(s.elapsed_time(e) for s, e in evs)
+            tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            uu = torch.tensor([float(done_units)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+            total_ms, all_units = float(tt), float(uu)
+            value = all_units / (total_ms * 1e-3)
+        except Exception as ex:  # keep the eager numbers
+            eval_keys, graph_err = None, repr(ex)
 
     # ---- end-to-end through the public API with host buffers (H2D + step + D2H of loss/logits)
     h2d = hbs[0].h2d_bytes()
@@ -638,8 +676,12 @@ def run_b200(args):
         if graph_keys is not None:  # refresh the graph's static input buffers, then replay
             hbs[i % nb].copy_into(dbs[i % nb])
             return trainer.replay(graph_keys[i % nb])
-        if not train:  # inference: chunked upload overlapped with the forward (Trainer.eval_step_host)
-            return None, trainer.eval_step_host(hbs[i % nb])
+        if not train:
+            hb = hbs[i % nb]
+            if eval_keys is not None and hb.clouds.numel() * 4 < CloudEmbedder.PIPELINE_MIN_BYTES:
+                hb.copy_into(dbs[i % nb])  # small batch: refresh the graph's static inputs, replay
+                return None, trainer.replay_eval(eval_keys[i % nb])
+            return None, trainer.eval_step_host(hb)  # large: chunked upload overlapped with the forward
         return step(hbs[i % nb].to_device(dev))
 
     for i in range(0 if args.no_e2e else max(3, args.warmup // 2)):
@@ -676,7 +718,7 @@ def run_b200(args):
                 "ms_per_step": float(t2) / args.steps},
         "rates": rates(counts, world, total_ms / args.steps),
         "gpu_launches": int(launches),
-        "cuda_graph": graph_keys is not None,
+        "cuda_graph": graph_keys is not None or eval_keys is not None,
         "eager": {"ms_per_step": eager_ms, "value": eager_value},
         "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
         "clocks": clocks,

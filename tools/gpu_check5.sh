@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_shapes.py tests/test_bf16.py -m gpu -q -x --timeout 600 > gpurun_out/chk5_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/chk5_pytest.log
+tail -6 gpurun_out/chk5_pytest.log
+for spec in "room_fwd 1536 30" "vkitti_eval 8192 30" "sema3d_eval 20000 20"; do set -- $spec
+timeout 600 python bench.py --workload $1 --nodes $2 --steps $3 --warmup 8 --no-roofline --no-cpu-baseline > gpurun_out/chk5_$1.json 2> gpurun_out/chk5_$1.err
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/chk5_$1.json').read().strip().splitlines()[-1])
+    print('$1', round(d['ms_per_step'],4), 'eager', round(d['eager']['ms_per_step'],4), 'e2e', round(d['e2e'].get('ms_per_step',0),4), 'launches', d['gpu_launches'], 'graph', d['cuda_graph'], d.get('cuda_graph_error'), 'parity', d.get('parity_rel_err'))
+except Exception as ex:
+    print('$1 FAILED', ex); print(open('gpurun_out/chk5_$1.err').read()[-2500:])
+PY
+done
