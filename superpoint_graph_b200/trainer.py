@@ -167,7 +167,10 @@ class Trainer(object):
     def compute_gradients(self, db):
         """Forward, loss, backward; gathers every parameter gradient into the flat buffer.
         Returns (loss[1], logits).  Purely local to this rank (no collective)."""
-        ops.set_pdl(0 if self._side is not None else 1)  # launch policy measured per schedule, see ops.set_pdl
+        # launch policy (ops.set_pdl): programmatic dependent launch measured 2 % SLOWER on the training step —
+        # for the whole step and for the forward phase alone (profiles/r2_pdl_policy_ab.log) — so it is off
+        # here; the inference paths leave it on
+        ops.set_pdl(0)
         try:
             return self._compute_gradients(db)
         finally:
