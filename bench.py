@@ -734,7 +734,8 @@ def run_b200(args):
         ops.prof_reset()
         ops.prof_enable(1)
         flops0 = {"gemm_f32": ops.GEMM_FLOPS[0] - ops.TC_FLOPS[0] - ops.DW_FLOPS[0],
-                  "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0]}
+                  "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0],
+                  "pointnet_fused_eval": ops.FUSED_FLOPS[0]}
         nprof = 3
         for i in range(nprof):
             step(dbs[i % nb]) if world == 1 else None
@@ -747,13 +748,18 @@ def run_b200(args):
             line["kernel_shares"] = {k: {"launches_per_step": v[0] / nprof, "ms_per_step": v[1] / nprof,
                                          "share": v[1] / tot} for k, v in top[:12]}
             flops1 = {"gemm_f32": ops.GEMM_FLOPS[0] - ops.TC_FLOPS[0] - ops.DW_FLOPS[0],
-                      "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0]}
+                      "tc_gemm_3xtf32": ops.TC_FLOPS[0], "tc_dw_3xtf32": ops.DW_FLOPS[0],
+                      "pointnet_fused_eval": ops.FUSED_FLOPS[0]}
             notes = {"gemm_f32": "exact-fp32 FMA GEMM (small/odd shapes), measured against the bf16 tensor peak",
                      "tc_gemm_3xtf32": "tcgen05 kind::tf32, 3 MMAs per product (error-compensated split, fp32-"
                                        "equivalent): algorithmic FLOPs counted once; ceiling = bf16 peak / 6",
-                     "tc_dw_3xtf32": "tcgen05 kind::tf32 MN-major operands, 3 MMAs per product; ceiling = bf16 peak / 6"}
+                     "tc_dw_3xtf32": "tcgen05 kind::tf32 MN-major operands, 3 MMAs per product; ceiling = bf16 peak / 6",
+                     "pointnet_fused_eval": ("fused eval trunk, tcgen05 kind::f16 on bf16 operands: ceiling = bf16 peak"
+                                             if w["dtype"] == "bf16" else
+                                             "fused eval trunk, tcgen05 kind::tf32, 3 MMAs per product (fp32-equivalent): "
+                                             "algorithmic FLOPs counted once; ceiling = bf16 peak / 6")}
             dense = {}
-            for name in ("tc_gemm_3xtf32", "tc_dw_3xtf32", "gemm_f32"):
+            for name in ("tc_gemm_3xtf32", "tc_dw_3xtf32", "gemm_f32", "pointnet_fused_eval"):
                 if name in ks and ks[name][1] > 0:
                     ach = (flops1[name] - flops0[name]) / (ks[name][1] * 1e-3) / 1e12
                     dense[name] = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
@@ -761,6 +767,8 @@ def run_b200(args):
                                    "share_of_step": ks[name][1] / tot, "note": notes[name]}
             for name, obj in dense.items():
                 tr = ncu_traffic().get(name)
+                if name == "pointnet_fused_eval" and w["dtype"] == "bf16":
+                    tr = None  # the committed ncu capture is of the fp32 (3xTF32) variant
                 if tr:
                     obj["traffic"] = tr["bytes_per_launch"]
                     obj["traffic_note"] = "ncu --set full, %s (%s); algorithmic %.4g B" % (

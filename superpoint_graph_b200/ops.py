@@ -936,4 +936,11 @@ def pointnet_fused_eval(clouds, T, image, bias, widths, pooled, ldp):
     name = "spg_pointnet_fused_eval_bf16" if image.dtype == torch.bfloat16 else "spg_pointnet_fused_eval"
     _lib.call(name, clouds, B, F, L, None if T is None else _c(T), 1, image, bias,
               int(widths.numel()), widths.data_ptr(), pooled, ldp, _lib.current_stream())
+    k = int(F)
+    for n in widths.tolist():  # algorithmic FLOPs of the chain (valid K of the first layer, no padding)
+        FUSED_FLOPS[0] += 2 * B * L * k * int(n)
+        k = int(n)
     return pooled
+
+
+FUSED_FLOPS = [0]  # algorithmic FLOPs through the fused eval trunk; read by bench.py

@@ -261,7 +261,7 @@ def test_sema3d_eval_chunked_vs_oracle(dev, monkeypatch):
     # the pipelined upload (chunks on a copy stream, PointNet per chunk, filter networks underneath) is the
     # same forward; thresholds lowered so that this 15 MB batch takes it, in 3 chunks
     monkeypatch.setattr(spg_pointnet.CloudEmbedder, "PIPELINE_MIN_BYTES", 1 << 20)
-    monkeypatch.setattr(spg_pointnet.CloudEmbedder, "PIPELINE_CHUNK_BYTES", 5 << 20)
+    monkeypatch.setattr(spg_pointnet.CloudEmbedder, "PIPELINE_CHUNK_BYTES", 4 << 20)
     assert hb.clouds.numel() * 4 >= 3 * spg_pointnet.CloudEmbedder.PIPELINE_CHUNK_BYTES
     for _ in range(2):  # second call: the copy stream and the allocator's blocks are reused
         piped = tr.eval_step_host(hb)
