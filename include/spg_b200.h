@@ -390,17 +390,19 @@ int spg_confusion_count(const float* logits, int64_t ld_logits, const int64_t* l
                         spg_stream_t stream);
 /* The step's only collective fused with the optimizer (ref: learning/main.py:210-213 on the averaged
  * gradient): one-shot all-reduce over NVLink peer memory + 1/world + element-wise clamp
- * + Adam in ONE kernel.  peer_grads: DEVICE array of `world` pointers to the ranks' flat gradient
- * buffers (symmetric memory, n floats each, 16-byte aligned); peer_flags: DEVICE array of `world`
- * pointers to zero-initialised symmetric uint32 buffers of spg_allreduce_flag_words(world) words;
- * local_state: 2 zero-initialised uint32 words in local device memory (launch epoch, block ticket);
- * step_counter as in spg_clamp_adam_dev.  All ranks must call it once per step, in the same order.
- * The sum runs in rank order: bit-identical on every rank.                                        */
+ * + Adam in ONE kernel.  grad: this rank's flat gradient (local memory, n floats, 16-byte aligned);
+ * peer_stage: DEVICE array of `world` pointers to the ranks' symmetric staging buffers of
+ * spg_allreduce_stage_floats(n) floats (two halves, used alternately: no "done reading" handshake);
+ * peer_flags: DEVICE array of `world` pointers to zero-initialised symmetric uint32 buffers of
+ * spg_allreduce_flag_words(world) words; local_state: 2 zero-initialised uint32 words in local device
+ * memory (launch epoch, block ticket); step_counter as in spg_clamp_adam_dev.  All ranks must call it once
+ * per step, in the same order.  The sum runs in rank order: bit-identical on every rank.            */
 int spg_allreduce_flag_words(int world);
-int spg_allreduce_clamp_adam(const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
-                             float* param, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, float grad_clip, float grad_scale,
-                             int64_t* step_counter, uint32_t* local_state, spg_stream_t stream);
+int64_t spg_allreduce_stage_floats(int64_t n);
+int spg_allreduce_clamp_adam(const float* grad, float* const* peer_stage, uint32_t* const* peer_flags, int rank,
+                             int world, float* param, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, float grad_clip,
+                             float grad_scale, int64_t* step_counter, uint32_t* local_state, spg_stream_t stream);
 /* Eval-mode PointNet trunk, fully fused (ref: learning/pointnet.py:55-61,120-127 under model.eval()):
  * for every superpoint b (n_points must be 128 = one tensor-core M tile, n_features <= 16):
  *   x = clouds[b] ([F, 128], NCL as the reference stacks them, learning/spg.py:162)

@@ -107,16 +107,18 @@ __global__ void counter_increment_kernel(long long* counter) {
     SPG_PDL_ENTRY(); counter[0] += 1; }
 
 // ---- the step's only collective, fused with what follows it (main.py:210-213) ----------
-// One-shot all-reduce over NVLink peer memory + average + element-wise clamp + Adam in ONE kernel:
-// every rank's flat gradient lives in symmetric memory (peer pointers in `peer_grads`), every rank reads
-// all `world` copies of its slice directly over NVLink, sums them in rank order (deterministic and
-// bit-identical on all ranks, so the replicas cannot drift), scales by 1/world, clamps and applies Adam
-// to its own replica.  0.85 MB per rank: latency-, not bandwidth-bound, hence one-shot and no NCCL launch.
-// Cross-GPU ordering: block b of every rank exchanges release/acquire flags (system scope) with block b
-// of every peer before reading ("your gradient gather has finished": stream order + the flag) and after
-// ("I am done reading, you may overwrite").  Flags carry a launch epoch kept in device memory, so the
-// kernel can sit inside a CUDA graph.  Blocks only ever wait for same-index blocks of PEERS, never for
-// local blocks: no co-residency requirement.
+// One-shot all-reduce over NVLink peer memory + average + element-wise clamp + Adam in ONE kernel.
+// Every rank owns a symmetric STAGING buffer of two halves (peer pointers in `peer_stage`).  Block b
+//   0. copies its slice of the local flat gradient into half (epoch & 1) of its own staging buffer,
+//   1. tells block b of every peer "my slice is there" (release flag, system scope) and waits for theirs,
+//   2. reads the same slice from every peer's half over NVLink, sums in rank order (deterministic and
+//      bit-identical on all ranks: the replicas cannot drift), scales by 1/world, clamps, applies Adam.
+// There is no second ("done reading") handshake: a rank overwrites half h again two launches later, and it
+// cannot finish the launch in between before every peer has STARTED that launch, i.e. finished this one
+// (stream order) and with it all reads of half h.  0.85 MB per rank: latency-, not bandwidth-bound, hence one-shot
+// and no NCCL launch.  Flags carry a launch epoch kept in device memory, so the kernel can sit inside a CUDA
+// graph.  Blocks only ever wait for same-index blocks of PEERS, never for local blocks: no co-residency
+// requirement.
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -127,32 +129,45 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 }
 
 __global__ void __launch_bounds__(512)
-allreduce_clamp_adam_kernel(const float* const* __restrict__ peer_grads, unsigned* const* __restrict__ peer_flags,
-                            int rank, int world, float* __restrict__ p, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
-                            float clip, float gscale, long long* __restrict__ counter,
-                            unsigned* __restrict__ epoch_ptr, unsigned* __restrict__ ticket) {
+allreduce_clamp_adam_kernel(const float* __restrict__ grad_local, float* const* __restrict__ peer_stage,
+                            unsigned* const* __restrict__ peer_flags, int rank, int world, float* __restrict__ p,
+                            float* __restrict__ m, float* __restrict__ v, int64_t n, int64_t half_stride, float lr,
+                            float b1, float b2, float eps, float wd, float clip, float gscale,
+                            long long* __restrict__ counter, unsigned* __restrict__ epoch_ptr,
+                            unsigned* __restrict__ ticket) {
     SPG_PDL_ENTRY();
     const unsigned epoch = epoch_ptr[0] + 1u;
     const unsigned nb = gridDim.x;
+    const int64_t half = (int64_t)(epoch & 1u) * half_stride;
     unsigned* my_flags = peer_flags[rank];
-    // phase 1: "my gradients are complete" to block b of every peer; wait for the same from every peer
+    float* my_stage = peer_stage[rank] + half;
+    const int64_t n4 = n >> 2;
+    // step 0: my slice into my staging half
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)nb * blockDim.x)
+        reinterpret_cast<float4*>(my_stage)[i] = reinterpret_cast<const float4*>(grad_local)[i];
+    if (blockIdx.x == 0)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) my_stage[i] = grad_local[i];
+    __syncthreads();
+    // step 1: "my slice is complete" to block b of every peer; wait for the same from every peer
     if (threadIdx.x < world) {
         const int peer = threadIdx.x;
         __threadfence_system();
         st_release_sys(peer_flags[peer] + (size_t)blockIdx.x * world + rank, epoch);
-        while (ld_acquire_sys(my_flags + (size_t)blockIdx.x * world + peer) != epoch) {
+        // ">= epoch" (wrap-around safe), not "== epoch": a peer that is already one launch ahead has
+        // overwritten its flag with epoch + 1; its half for THIS epoch is intact until it passes the
+        // handshake of that next launch, which needs this rank to get there too
+        while ((int)(ld_acquire_sys(my_flags + (size_t)blockIdx.x * world + peer) - epoch) < 0) {
         }
     }
     __syncthreads();
     const double step = (double)(counter[0] + 1);
     const float bc1 = (float)(1.0 - pow((double)b1, step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
-    const int64_t n4 = n >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)nb * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < world; ++r) {
-            const float4 q = __ldcg(reinterpret_cast<const float4*>(peer_grads[r]) + i);
+            const float4 q = r == rank ? reinterpret_cast<const float4*>(grad_local)[i]
+                                       : __ldcg(reinterpret_cast<const float4*>(peer_stage[r] + half) + i);
             g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
         }
         float gv[4] = {g.x, g.y, g.z, g.w};
@@ -176,7 +191,7 @@ allreduce_clamp_adam_kernel(const float* const* __restrict__ peer_grads, unsigne
     if (blockIdx.x == 0) {  // tail (n % 4 elements)
         for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
             float gi = 0.f;
-            for (int r = 0; r < world; ++r) gi += __ldcg(peer_grads[r] + i);
+            for (int r = 0; r < world; ++r) gi += r == rank ? grad_local[i] : __ldcg(peer_stage[r] + half + i);
             gi *= gscale;
             if (clip > 0.f && gi == gi) gi = fminf(fmaxf(gi, -clip), clip);
             const float pi = p[i];
@@ -185,15 +200,6 @@ allreduce_clamp_adam_kernel(const float* const* __restrict__ peer_grads, unsigne
             m[i] = mi;
             v[i] = vi;
             p[i] = pi - (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-        }
-    }
-    __syncthreads();
-    // phase 2: "I have read your gradients" (second flag bank), wait for every peer's
-    if (threadIdx.x < world) {
-        const int peer = threadIdx.x;
-        unsigned* bank = peer_flags[peer] + (size_t)nb * world;
-        st_release_sys(bank + (size_t)blockIdx.x * world + rank, epoch);
-        while (ld_acquire_sys(my_flags + (size_t)nb * world + (size_t)blockIdx.x * world + peer) != epoch) {
         }
     }
     __syncthreads();
@@ -269,24 +275,26 @@ int spg_clamp_adam_dev(float* param, const float* grad, float* exp_avg, float* e
 }
 
 
-int spg_allreduce_flag_words(int world) { return 2 * 2 * kNumSMs * world + 8; }
+int spg_allreduce_flag_words(int world) { return 2 * kNumSMs * world + 8; }
 
-int spg_allreduce_clamp_adam(const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
-                             float* param, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, float grad_clip, float grad_scale,
-                             int64_t* step_counter, uint32_t* local_state, spg_stream_t stream) {
+int64_t spg_allreduce_stage_floats(int64_t n) { return n < 0 ? 0 : 2 * ((n + 3) / 4 * 4); }
+
+int spg_allreduce_clamp_adam(const float* grad, float* const* peer_stage, uint32_t* const* peer_flags, int rank,
+                             int world, float* param, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, float grad_clip,
+                             float grad_scale, int64_t* step_counter, uint32_t* local_state, spg_stream_t stream) {
     if (n < 0 || world < 1 || world > 32 || rank < 0 || rank >= world) return SPG_E_BADARG;
     if (n == 0) return SPG_OK;
-    if (!peer_grads || !peer_flags || !param || !exp_avg || !exp_avg_sq || !step_counter || !local_state)
+    if (!grad || !peer_stage || !peer_flags || !param || !exp_avg || !exp_avg_sq || !step_counter || !local_state)
         return SPG_E_BADARG;
-    if (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return SPG_E_ALIGN;
+    if (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)grad) & 15) return SPG_E_ALIGN;
     int64_t blocks = ceil_div64(ceil_div64(n, 4), 512);
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
     if (blocks < 1) blocks = 1;
-    SPG_LAUNCH(K_CLAMP_ADAM, (cudaStream_t)stream, allreduce_clamp_adam_kernel, (unsigned)blocks, 512, 0,
-               peer_grads, (unsigned* const*)peer_flags, rank, world, param, exp_avg, exp_avg_sq, n, lr, beta1,
-               beta2, eps, weight_decay, grad_clip, grad_scale, (long long*)step_counter,
-               (unsigned*)local_state, (unsigned*)local_state + 1);
+    SPG_LAUNCH(K_CLAMP_ADAM, (cudaStream_t)stream, allreduce_clamp_adam_kernel, (unsigned)blocks, 512, 0, grad,
+               peer_stage, (unsigned* const*)peer_flags, rank, world, param, exp_avg, exp_avg_sq, n,
+               (n + 3) / 4 * 4, lr, beta1, beta2, eps, weight_decay, grad_clip, grad_scale,
+               (long long*)step_counter, (unsigned*)local_state, (unsigned*)local_state + 1);
     return launch_status();
 }
 

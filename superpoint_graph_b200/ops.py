@@ -674,23 +674,26 @@ def clamp_adam_dev_(param, grad, exp_avg, exp_avg_sq, step_counter, lr, beta1=0.
 
 
 class FusedAllreduce(object):
-    """Symmetric-memory plumbing of spg_allreduce_clamp_adam: the flat gradient buffer and the flag words
-    are allocated with torch.distributed._symmetric_memory (CUDA VMM handles exchanged through the process
-    group's store) so that every rank holds device pointers to every peer's copy over NVLink."""
+    """Symmetric-memory plumbing of spg_allreduce_clamp_adam: a two-half staging buffer and the flag words are
+    allocated with torch.distributed._symmetric_memory (CUDA VMM handles exchanged through the process
+    group's store) so that every rank holds device pointers to every peer's copy over NVLink.  `grad` — the
+    flat gradient the step writes — is ordinary local memory; the kernel stages it itself."""
 
     def __init__(self, n, device, group):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.grad = symm_mem.empty(n, dtype=torch.float32, device=device)
-        self.grad.zero_()
+        self.grad = torch.zeros(n, dtype=torch.float32, device=device)
+        self.stage = symm_mem.empty(int(_lib.lib().spg_allreduce_stage_floats(int(n))), dtype=torch.float32,
+                                    device=device)
+        self.stage.zero_()
         words = int(_lib.lib().spg_allreduce_flag_words(self.world))
         self.flags = symm_mem.empty(words, dtype=torch.int32, device=device)
         self.flags.zero_()
-        self._h_grad = symm_mem.rendezvous(self.grad, group)
+        self._h_stage = symm_mem.rendezvous(self.stage, group)
         self._h_flags = symm_mem.rendezvous(self.flags, group)
-        self.grad_ptrs = int(self._h_grad.buffer_ptrs_dev)
+        self.stage_ptrs = int(self._h_stage.buffer_ptrs_dev)
         self.flag_ptrs = int(self._h_flags.buffer_ptrs_dev)
         self.state = torch.zeros(2, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
@@ -699,8 +702,8 @@ class FusedAllreduce(object):
     def step_(self, param, exp_avg, exp_avg_sq, step_counter, lr, beta1=0.9, beta2=0.999, eps=1e-8,
               weight_decay=0.0, grad_clip=0.0):
         _need_cuda(param, exp_avg, exp_avg_sq, step_counter)
-        _lib.call("spg_allreduce_clamp_adam", self.grad_ptrs, self.flag_ptrs, self.rank, self.world, param,
-                  exp_avg, exp_avg_sq, param.numel(), float(lr), float(beta1), float(beta2), float(eps),
+        _lib.call("spg_allreduce_clamp_adam", self.grad, self.stage_ptrs, self.flag_ptrs, self.rank, self.world,
+                  param, exp_avg, exp_avg_sq, param.numel(), float(lr), float(beta1), float(beta2), float(eps),
                   float(weight_decay), float(grad_clip), 1.0 / self.world, step_counter, self.state,
                   _lib.current_stream())
 
