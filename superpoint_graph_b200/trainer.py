@@ -155,7 +155,8 @@ class Trainer(object):
         self.embedder = CloudEmbedder(SimpleNamespace(cuda=1, ptn_mem_monger=args.ptn_mem_monger))
 
     def forward(self, db):
-        self.model.ecc.gconvs[0].set_info(db.gi)
+        for gc in self.model.ecc.gconvs:  # one batched graph, shared by every convolution of the model
+            gc.set_info(db.gi)
         if ops.SIDE[0] is not None:  # filter networks run underneath the PointNet forward
             for gc in self.model.ecc.gconvs:
                 if hasattr(gc, "prefetch_filters"):
@@ -337,7 +338,8 @@ class Trainer(object):
             if hb.clouds.numel() * hb.clouds.element_size() < CloudEmbedder.PIPELINE_MIN_BYTES:
                 return self.forward(hb.to_device(dev))
             d = hb.to_device(dev, skip=("clouds", "clouds_global"))
-            self.model.ecc.gconvs[0].set_info(d.gi)
+            for gc in self.model.ecc.gconvs:
+                gc.set_info(d.gi)
 
             def filters():
                 for gc in self.model.ecc.gconvs:
