@@ -486,6 +486,10 @@ def loader_roofline(dev, pk, with_cpu):
     out = {"kernel": "cloud_build", "bound": "hbm", "superpoints": nv, "points_resident": int(counts.sum()),
            "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
            "frac": gbs / pk["hbm"], "traffic": None, "gpu_superpoints_per_s": nv / (ms * 1e-3)}
+    tr = ncu_traffic().get("cloud_build")
+    if tr:
+        out["traffic"] = tr["bytes_per_launch"]
+        out["traffic_note"] = "ncu --set full, %s (%s)" % (tr["launch"], tr["source"])
     if with_cpu:
         from oracle import loader_ref  # CPU baseline leg only
         n_cpu = 2000
