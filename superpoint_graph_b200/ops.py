@@ -67,10 +67,11 @@ def zero_(t):
 class EccGraph(object):
     """Device-side CSR views of one batched graph, shared by all ECC kernels.
 
-    Built on the host from the reference's `(idxn, idxe, degs)` triple
-    (ref: learning/ecc/GraphConvInfo.py:48-69): `tgt_rowptr` is the exclusive scan of the
-    in-degrees, `edge_tgt` the target of every edge, `(src_rowptr, src_perm)` a stable
-    source-sorted CSR used by the atomic-free grad_input kernel.
+    Derived from the reference's `(idxn, idxe, degs)` triple (ref: learning/ecc/GraphConvInfo.py:48-69):
+    `tgt_rowptr` is the exclusive scan of the in-degrees, `edge_tgt` the target of every edge,
+    `(src_rowptr, src_perm)` a stable source-sorted CSR used by the atomic-free grad_input kernel.
+    CUDA inputs: `EccGraph.from_device` (spg_graph_build, on the device); host inputs: this constructor
+    (numpy), which the CPU tests pin and the GPU tests compare the device builder with, bit for bit.
     """
 
     def __init__(self, idxn, idxe, degs, n_in=None):

@@ -80,7 +80,8 @@ class GraphConvInfo(object):
         return gi
 
     def graph(self):
-        """The device CSR bundle (built once per batch, on the host, from idxn/degs)."""
+        """The CSR bundle the kernels read (built once per batch from idxn/degs: on the device by cuda(),
+        else on first use from the host arrays)."""
         if self._graph is None:
             self._graph = ops.EccGraph(self._idxn, self._idxe, self._degrees,
                                        n_in=int(self._degrees.numel()))

@@ -214,3 +214,38 @@ def test_synthetic_batch_shapes():
     assert all(torch.equal(b[k], b2[k]) for k in b)
     xyz = b["clouds"][:, :3, :]
     assert float(xyz.abs().max()) <= 1.0 + 1e-5 and abs(float(xyz.mean())) < 1e-3
+
+
+def test_host_batch_validates_the_collated_graph_arrays():
+    """HostBatch checks (idxn, degs) once on the host (the device builder then runs unchecked)."""
+    from superpoint_graph_b200.synthetic import make_batch
+    from superpoint_graph_b200.trainer import HostBatch
+    b = make_batch(n_nodes=40, seed=3, nfeat=14, n_classes=13, minpts=40)
+    hb = HostBatch(b)
+    assert hb.idxn.dtype == torch.int64 and hb.degs.dtype == torch.int64
+    assert int(hb.degs.sum()) == hb.idxn.numel()
+    assert hb.h2d_bytes() == sum(getattr(hb, f).numel() * getattr(hb, f).element_size() for f in HostBatch.FIELDS)
+    bad = dict(b)
+    bad["idxn"] = b["idxn"].clone()
+    bad["idxn"][0] = 40
+    with pytest.raises(ValueError, match="idxn out of range"):
+        HostBatch(bad)
+    bad = dict(b)
+    bad["degs"] = b["degs"].clone()
+    bad["degs"][0] += 1
+    with pytest.raises(ValueError, match="does not match the number of edges"):
+        HostBatch(bad)
+
+
+def test_launch_policy_switch_is_a_host_side_setter(monkeypatch):
+    """spg_set_pdl needs no device; an explicit SPG_PDL in the environment makes ops.set_pdl a no-op."""
+    from superpoint_graph_b200 import _lib, ops
+    _lib.call("spg_set_pdl", 0)
+    _lib.call("spg_set_pdl", 1)
+    calls = []
+    monkeypatch.setattr(_lib, "call", lambda name, *a: calls.append((name, a)))
+    monkeypatch.delenv("SPG_PDL", raising=False)
+    ops.set_pdl(0)
+    monkeypatch.setenv("SPG_PDL", "1")
+    ops.set_pdl(0)
+    assert calls == [("spg_set_pdl", (0,))]
